@@ -1,0 +1,236 @@
+/* include/dabgpu.h -- C ABI of libdabgpu.so, the B200 (sm_100a) DAB receive path.
+ *
+ * This is the drop-in boundary behind the reference's C++ classes.  Every entry point lists the
+ * reference interface it replaces (paths relative to /root/reference/vendor/DAB-Radio/src unless
+ * noted).  The reference classes are one-object-per-stream and synchronous; the ABI is the same
+ * contract batched over many independent streams ("stream" = one tuner / one ensemble).
+ *
+ * Conventions
+ *   - every function returns DABGPU_OK (0) or a negative dabgpu_status; nothing throws;
+ *     dabgpu_last_error() gives a thread-local message for the last failure.
+ *   - all buffers are caller-allocated plain memory; "host" pointers may be pageable or pinned,
+ *     "device" pointers must belong to the context's CUDA device.
+ *   - soft bits are int8: +127 = logical 1, -127 = logical 0, 0 = punctured (viterbi_config.h:11-14).
+ *   - there is NO CPU fallback: without a CUDA device dabgpu_ctx_create fails with DABGPU_ERR_CUDA.
+ */
+#ifndef DABGPU_H
+#define DABGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DABGPU_API __attribute__((visibility("default")))
+
+typedef enum {
+    DABGPU_OK = 0,
+    DABGPU_ERR_INVALID = -1,   /* bad argument (e.g. invalid transmission mode: dab_ofdm_params_ref.cpp:53-54) */
+    DABGPU_ERR_CUDA = -2,      /* CUDA runtime/driver failure or no device */
+    DABGPU_ERR_NOMEM = -3,
+    DABGPU_ERR_STATE = -4,     /* call not valid in the current state (e.g. nothing configured) */
+    DABGPU_ERR_OVERFLOW = -5   /* caller buffer or internal queue too small */
+} dabgpu_status;
+
+typedef struct dabgpu_ctx dabgpu_ctx;
+
+/* ---------------------------------------------------------------------------------------------
+ * Context
+ * ------------------------------------------------------------------------------------------- */
+enum { DABGPU_IQ_U8 = 0, DABGPU_IQ_C32 = 1 };
+
+/* Synchronisation knobs = OFDM_Demod_Config (ofdm/ofdm_demodulator.h:24-45), same defaults. */
+typedef struct {
+    float signal_l1_update_beta;      /* 0.95 */
+    int   signal_l1_nb_samples;       /* 100  */
+    int   signal_l1_nb_decimate;      /* 5    */
+    float null_thresh_start;          /* 0.35 */
+    float null_thresh_end;            /* 0.75 */
+    float fine_freq_update_beta;      /* 0.9  */
+    int   is_coarse_freq_correction;  /* 1    */
+    float max_coarse_freq_correction_norm; /* 0.5 */
+    float coarse_freq_slow_beta;      /* 0.1  */
+    float impulse_peak_threshold_db;  /* 20   */
+    float impulse_peak_distance_probability; /* 0.15 */
+} dabgpu_ofdm_config;
+
+typedef struct {
+    int device;            /* CUDA device ordinal */
+    int transmission_mode; /* 1..4 (get_DAB_OFDM_params / get_dab_parameters) */
+    int max_streams;       /* independent IQ streams held by this context */
+    int iq_format;         /* DABGPU_IQ_U8 (2 B/sample, converted on device like app_iq_readers.h:23-43,72-87) or DABGPU_IQ_C32 */
+    size_t ring_samples;   /* per-stream IQ ring capacity in samples, power of two; 0 = 4 frames rounded up */
+    int frame_slots;       /* soft-bit frame ring depth per stream (>= 8, power of two); 0 = 8 */
+    int max_subchannels;   /* sub-channel table size per stream; 0 = 64 */
+    void* cuda_stream;     /* optional cudaStream_t owned by the caller; NULL = library creates one */
+    dabgpu_ofdm_config ofdm;
+} dabgpu_config;
+
+DABGPU_API const char* dabgpu_version(void);
+DABGPU_API const char* dabgpu_last_error(void);
+DABGPU_API int dabgpu_device_count(void);
+DABGPU_API void dabgpu_config_default(dabgpu_config* cfg, int transmission_mode);
+DABGPU_API int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out);
+DABGPU_API void dabgpu_ctx_destroy(dabgpu_ctx* ctx);
+DABGPU_API int dabgpu_sync(dabgpu_ctx* ctx);                       /* wait for all queued work */
+DABGPU_API void* dabgpu_cuda_stream(dabgpu_ctx* ctx);              /* the stream every kernel is launched on */
+/* number of kernels of this library launched on the context so far (bench.py "gpu_launches") */
+DABGPU_API uint64_t dabgpu_launch_count(const dabgpu_ctx* ctx);
+
+/* Frame geometry: OFDM_Params (ofdm/ofdm_params.h) + DAB_Parameters (dab/constants/dab_parameters.h:5-24) */
+typedef struct {
+    int nb_frame_symbols, nb_symbol_period, nb_null_period, nb_cyclic_prefix, nb_fft, nb_data_carriers;
+    int nb_frame_bits, nb_fic_bits, nb_msc_bits, nb_cifs, nb_fibs_per_cif, nb_fib_group_bits, nb_cif_bits;
+    int nb_frame_samples;
+} dabgpu_params;
+DABGPU_API int dabgpu_get_params(int transmission_mode, dabgpu_params* out);
+
+/* ---------------------------------------------------------------------------------------------
+ * OFDM demodulation.  Replaces OFDM_Demod::{Process,Reset,On_OFDM_Frame,Get*}
+ * (ofdm/ofdm_demodulator.h:109-141, ofdm_demodulator.cpp:235-950) with the canonical
+ * serialised ordering of SURVEY.md appendix C: a completed frame is fully demodulated (and the
+ * fine frequency updated) before the next sample of that stream is consumed.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int state;                 /* OFDM_Demod::State numbering (ofdm_demodulator.h:50-56) */
+    int total_frames_read;
+    int total_frames_desync;
+    int fine_time_offset;
+    float signal_l1_average;
+    float freq_coarse_offset;
+    float freq_fine_offset;
+    int frames_queued;         /* soft-bit frames produced and not yet popped */
+} dabgpu_ofdm_status;
+
+/* OFDM_Demod::Reset() for one stream (-1 = all streams) */
+DABGPU_API int dabgpu_ofdm_reset(dabgpu_ctx* ctx, int stream);
+
+/* OFDM_Demod::Process(block) for streams [first_stream, first_stream+n_streams): copies n_samples
+ * per stream from host memory (stream i at iq_host + i*stream_stride_bytes) into the device IQ
+ * rings and consumes them.  The samples are presented to the state machine as consecutive
+ * Process() calls of block_size samples (the reference's results depend on that partition while
+ * acquiring; the CLI default is 65536).  block_size <= 0 means one block. */
+DABGPU_API int dabgpu_ofdm_process(dabgpu_ctx* ctx, const void* iq_host, size_t stream_stride_bytes,
+                                   int first_stream, int n_streams, int n_samples, int block_size);
+
+/* Same, for IQ already resident in device memory (no copy): the caller's buffer replaces the
+ * internal rings.  Layout: stream i sample k at d_iq + (i*stream_stride_samples + (k mod capacity))
+ * * bytes_per_sample, k = absolute sample index since attach.  capacity must be a power of two or
+ * >= every absolute index ever consumed. */
+DABGPU_API int dabgpu_ofdm_attach_device_input(dabgpu_ctx* ctx, const void* d_iq, size_t stream_stride_samples,
+                                               size_t capacity_samples);
+DABGPU_API int dabgpu_ofdm_advance(dabgpu_ctx* ctx, int first_stream, int n_streams, int n_samples, int block_size);
+
+/* On_OFDM_Frame: number of undelivered soft-bit frames per stream, then copy them out in order.
+ * Each frame is nb_frame_bits int8.  infos (optional) receives per-frame {coarse, fine} offsets
+ * and fine time offset as observed when the frame was emitted. */
+typedef struct { float freq_coarse_offset, freq_fine_offset; int fine_time_offset; int frame_index; } dabgpu_frame_info;
+DABGPU_API int dabgpu_ofdm_get_status(dabgpu_ctx* ctx, int stream, dabgpu_ofdm_status* out);
+DABGPU_API int dabgpu_ofdm_pop_frames(dabgpu_ctx* ctx, int stream, int8_t* frames_host, int max_frames,
+                                      dabgpu_frame_info* infos, int* n_frames_out);
+/* Bulk variant used by throughput harnesses: newest frame of every stream in [first, first+n) that
+ * produced one during the last process/advance call is copied to frames_host + i*nb_frame_bits;
+ * produced[i] = 1/0. */
+DABGPU_API int dabgpu_ofdm_fetch_latest(dabgpu_ctx* ctx, int first_stream, int n_streams, int8_t* frames_host,
+                                        uint8_t* produced);
+
+/* ---------------------------------------------------------------------------------------------
+ * Viterbi.  Replaces DAB_Viterbi_Decoder::{reset,update,chainback}
+ * (dab/algorithms/dab_viterbi_decoder.h:22-33; decoder selected at dab_viterbi_decoder.cpp:51-73 =
+ * ViterbiDecoder_AVX_u16<7,4>: saturating u16 metrics, tie => decision 1, renormalise at 60455).
+ * One job = reset(); update(seg 0..n_seg-1); chainback(n_out_bytes).
+ * ------------------------------------------------------------------------------------------- */
+#define DABGPU_MAX_SEGMENTS 5
+typedef struct {
+    uint64_t soft_offset;       /* offset of the first punctured symbol inside the soft buffer */
+    uint32_t n_soft;            /* punctured symbols available to this job */
+    uint32_t n_seg;
+    uint8_t  seg_pi[DABGPU_MAX_SEGMENTS + 3];   /* 1..24 = PI_TABLE row (puncture_codes.h:42-67), 0 = PI_X tail code */
+    uint32_t seg_bits[DABGPU_MAX_SEGMENTS];     /* requested_output_symbols of each update() call (multiple of 4) */
+    uint64_t out_offset;        /* byte offset inside the output buffer */
+    uint32_t n_out_bytes;       /* chainback length in bytes */
+    uint32_t descramble;        /* != 0: XOR with the energy-dispersal PRBS (additive_scrambler.h:10-36) */
+} dabgpu_viterbi_job;
+
+/* soft_host/out_host/path_error_host are host buffers; path_error_host (optional) gets the value
+ * chainback() returns (accumulated renormalisation bias + final state-0 metric). */
+DABGPU_API int dabgpu_viterbi_decode(dabgpu_ctx* ctx, const dabgpu_viterbi_job* jobs, int n_jobs,
+                                     const int8_t* soft_host, size_t soft_bytes,
+                                     uint8_t* out_host, size_t out_bytes, uint64_t* path_error_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Channel decode of whole transmission frames.
+ *   FIC  : replaces BasicFICRunner::Process + FIC_Decoder::DecodeFIBGroup (dab/fic/fic_decoder.cpp:53-117)
+ *   MSC  : replaces MSC_Decoder::DecodeCIF = CIF_Deinterleaver + EEP/UEP depuncture + Viterbi + descramble
+ *          (dab/msc/msc_decoder.cpp:46-154, dab/msc/cif_deinterleaver.cpp:20-71)
+ *   DAB+ : replaces AAC_Frame_Processor::Process through RS(120,110), fire code and AU CRC
+ *          (dab/audio/aac_frame_processor.cpp:126-362, dab/algorithms/reed_solomon_decoder.cpp:192-477)
+ * Frames are taken from the per-stream soft-bit frame ring, which is filled either by the OFDM
+ * stage on the device or by dabgpu_softbits_push (the BasicRadio::Process(span<viterbi_bit_t>) seam,
+ * basic_radio/basic_radio.cpp:41-65).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int start_address;   /* in capacity units (64 soft bits) */
+    int length;          /* in capacity units */
+    int is_uep;
+    int uep_prot_index;  /* UEP_PROTECTION_TABLE row (subchannel_protection_tables.h:21-86) */
+    int eep_prot_level;  /* 0..3 = level 1..4 */
+    int eep_type_b;      /* 0 = EEP-A, 1 = EEP-B */
+    int is_dabplus;      /* run the DAB+ superframe stage on this sub-channel */
+} dabgpu_subchannel;
+
+/* (Re)creates the MSC_Decoder set of one stream; deinterleaver / superframe state starts empty. */
+DABGPU_API int dabgpu_msc_configure(dabgpu_ctx* ctx, int stream, const dabgpu_subchannel* subs, int n_subs);
+
+/* BasicRadio::Process: one frame of nb_frame_bits int8 per stream, stream i at frames_host + i*stride */
+DABGPU_API int dabgpu_softbits_push(dabgpu_ctx* ctx, const int8_t* frames_host, size_t stream_stride_bytes,
+                                    int first_stream, int n_streams);
+
+/* Decodes, for every stream in [first, first+n), the oldest frame in its ring that has not been
+ * channel-decoded yet (streams without one are skipped).  Results stay on the device until fetched. */
+DABGPU_API int dabgpu_chan_decode(dabgpu_ctx* ctx, int first_stream, int n_streams);
+
+/* Result of the last dabgpu_chan_decode for one stream. */
+typedef struct {
+    int decoded;             /* 1 if a frame of this stream was decoded by the last call */
+    int frame_index;         /* index of that frame since context creation */
+} dabgpu_chan_status;
+DABGPU_API int dabgpu_chan_get_status(dabgpu_ctx* ctx, int stream, dabgpu_chan_status* out);
+/* fibs_host: nb_cifs*nb_fibs_per_cif*32 bytes (30 data + 2 CRC, descrambled); crc_ok: one byte per FIB */
+DABGPU_API int dabgpu_chan_get_fic(dabgpu_ctx* ctx, int stream, uint8_t* fibs_host, uint8_t* crc_ok);
+/* out_host: nb_cifs * bytes_per_cif decoded+descrambled bytes; valid[c] = 0 while the 16-CIF
+ * deinterleaver of this sub-channel is still filling (DecodeCIF returns an empty span) */
+DABGPU_API int dabgpu_chan_get_msc(dabgpu_ctx* ctx, int stream, int sub_index, uint8_t* out_host, size_t out_cap,
+                                   uint8_t* valid, int* bytes_per_cif);
+
+/* DAB+ superframe events of the last decoded frame, in the order AAC_Frame_Processor would have
+ * fired its observers (OnFirecodeError/OnRSError/OnSuperFrameHeader/OnAccessUnitCRCError/OnAccessUnit). */
+enum { DABGPU_EV_FIRECODE_ERROR = 1, DABGPU_EV_RS_ERROR = 2, DABGPU_EV_SUPERFRAME_HEADER = 3,
+       DABGPU_EV_AU_CRC_ERROR = 4, DABGPU_EV_ACCESS_UNIT = 5 };
+typedef struct { int32_t type, a, b, c, d, n_bytes; } dabgpu_event_header;  /* followed by n_bytes payload padded to 4 */
+DABGPU_API int dabgpu_chan_get_dabplus_events(dabgpu_ctx* ctx, int stream, int sub_index, uint8_t* log_host,
+                                              size_t log_cap, size_t* log_bytes);
+
+/* Reed_Solomon_Decoder::Decode batched (reed_solomon_decoder.h:18-26; GF(2^8)/0x11D, fcr 0, prim 1):
+ * n_codewords codewords of (255-pad) bytes each, corrected in place; counts[i] = return value of
+ * Decode (-1 = uncorrectable), positions (optional) = nroots ints per codeword (error locations incl. pad). */
+DABGPU_API int dabgpu_rs_decode(dabgpu_ctx* ctx, uint8_t* codewords_host, int n_codewords, int nroots, int pad,
+                                int* counts_host, int* positions_host);
+
+/* Whole-chain convenience for throughput runs: OFDM advance + channel decode of the frames produced. */
+typedef struct {
+    uint64_t frames_demodulated;   /* totals since context creation */
+    uint64_t frames_channel_decoded;
+    uint64_t fibs_crc_ok, fibs_total;
+    uint64_t msc_bytes_decoded;
+    uint64_t superframes_ok, superframes_rs_fail, superframes_firecode_fail;
+    uint64_t au_ok, au_crc_fail;
+} dabgpu_counters;
+DABGPU_API int dabgpu_get_counters(dabgpu_ctx* ctx, dabgpu_counters* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DABGPU_H */

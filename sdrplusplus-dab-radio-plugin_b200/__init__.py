@@ -1,0 +1,317 @@
+"""B200-native DAB receive path: thin Python binding of the C ABI in include/dabgpu.h.
+
+The product is csrc/libdabgpu.so (hand-written sm_100a kernels behind a C ABI).  This module only
+loads it with ctypes for tests and bench.py; there is no Python or CPU implementation of the path
+here, and loading fails loudly when the library has not been built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libdabgpu.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_OVERFLOW = 0, -1, -2, -3, -4, -5
+IQ_U8, IQ_C32 = 0, 1
+MAX_SEGMENTS = 5
+EV_FIRECODE_ERROR, EV_RS_ERROR, EV_SUPERFRAME_HEADER, EV_AU_CRC_ERROR, EV_ACCESS_UNIT = 1, 2, 3, 4, 5
+
+
+class DabGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"dabgpu error {code}: {msg}")
+        self.code = code
+
+
+class OfdmConfig(C.Structure):
+    _fields_ = [("signal_l1_update_beta", C.c_float), ("signal_l1_nb_samples", C.c_int), ("signal_l1_nb_decimate", C.c_int),
+                ("null_thresh_start", C.c_float), ("null_thresh_end", C.c_float), ("fine_freq_update_beta", C.c_float),
+                ("is_coarse_freq_correction", C.c_int), ("max_coarse_freq_correction_norm", C.c_float),
+                ("coarse_freq_slow_beta", C.c_float), ("impulse_peak_threshold_db", C.c_float),
+                ("impulse_peak_distance_probability", C.c_float)]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("transmission_mode", C.c_int), ("max_streams", C.c_int), ("iq_format", C.c_int),
+                ("ring_samples", C.c_size_t), ("frame_slots", C.c_int), ("max_subchannels", C.c_int),
+                ("cuda_stream", C.c_void_p), ("ofdm", OfdmConfig)]
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("nb_frame_symbols", "nb_symbol_period", "nb_null_period", "nb_cyclic_prefix", "nb_fft",
+                                       "nb_data_carriers", "nb_frame_bits", "nb_fic_bits", "nb_msc_bits", "nb_cifs",
+                                       "nb_fibs_per_cif", "nb_fib_group_bits", "nb_cif_bits", "nb_frame_samples")]
+
+
+class OfdmStatus(C.Structure):
+    _fields_ = [("state", C.c_int), ("total_frames_read", C.c_int), ("total_frames_desync", C.c_int), ("fine_time_offset", C.c_int),
+                ("signal_l1_average", C.c_float), ("freq_coarse_offset", C.c_float), ("freq_fine_offset", C.c_float),
+                ("frames_queued", C.c_int)]
+
+
+class FrameInfo(C.Structure):
+    _fields_ = [("freq_coarse_offset", C.c_float), ("freq_fine_offset", C.c_float), ("fine_time_offset", C.c_int), ("frame_index", C.c_int)]
+
+
+class ViterbiJob(C.Structure):
+    _fields_ = [("soft_offset", C.c_uint64), ("n_soft", C.c_uint32), ("n_seg", C.c_uint32), ("seg_pi", C.c_uint8 * (MAX_SEGMENTS + 3)),
+                ("seg_bits", C.c_uint32 * MAX_SEGMENTS), ("out_offset", C.c_uint64), ("n_out_bytes", C.c_uint32), ("descramble", C.c_uint32)]
+
+
+class SubchannelC(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("start_address", "length", "is_uep", "uep_prot_index", "eep_prot_level", "eep_type_b", "is_dabplus")]
+
+
+class ChanStatus(C.Structure):
+    _fields_ = [("decoded", C.c_int), ("frame_index", C.c_int)]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("frames_demodulated", "frames_channel_decoded", "fibs_crc_ok", "fibs_total", "msc_bytes_decoded",
+                                          "superframes_ok", "superframes_rs_fail", "superframes_firecode_fail", "au_ok", "au_crc_fail")]
+
+
+EXPORTS = [
+    "dabgpu_version", "dabgpu_last_error", "dabgpu_device_count", "dabgpu_config_default", "dabgpu_ctx_create", "dabgpu_ctx_destroy",
+    "dabgpu_sync", "dabgpu_cuda_stream", "dabgpu_launch_count", "dabgpu_get_params", "dabgpu_ofdm_reset", "dabgpu_ofdm_process",
+    "dabgpu_ofdm_attach_device_input", "dabgpu_ofdm_advance", "dabgpu_ofdm_get_status", "dabgpu_ofdm_pop_frames",
+    "dabgpu_ofdm_fetch_latest", "dabgpu_viterbi_decode", "dabgpu_msc_configure", "dabgpu_softbits_push", "dabgpu_chan_decode",
+    "dabgpu_chan_get_status", "dabgpu_chan_get_fic", "dabgpu_chan_get_msc", "dabgpu_chan_get_dabplus_events", "dabgpu_rs_decode",
+    "dabgpu_get_counters",
+]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads csrc/libdabgpu.so.  Raises if it was not built: there is no fallback implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DabGpuError(ERR_STATE, f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a). No CPU fallback exists.")
+    L = C.CDLL(LIB_PATH)
+    L.dabgpu_version.restype = C.c_char_p
+    L.dabgpu_last_error.restype = C.c_char_p
+    L.dabgpu_config_default.argtypes = [C.POINTER(Config), C.c_int]
+    L.dabgpu_config_default.restype = None
+    L.dabgpu_ctx_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    L.dabgpu_ctx_destroy.argtypes = [C.c_void_p]
+    L.dabgpu_ctx_destroy.restype = None
+    L.dabgpu_sync.argtypes = [C.c_void_p]
+    L.dabgpu_cuda_stream.argtypes = [C.c_void_p]
+    L.dabgpu_cuda_stream.restype = C.c_void_p
+    L.dabgpu_launch_count.argtypes = [C.c_void_p]
+    L.dabgpu_launch_count.restype = C.c_uint64
+    L.dabgpu_get_params.argtypes = [C.c_int, C.POINTER(Params)]
+    L.dabgpu_ofdm_reset.argtypes = [C.c_void_p, C.c_int]
+    L.dabgpu_ofdm_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.dabgpu_ofdm_attach_device_input.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    L.dabgpu_ofdm_advance.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.dabgpu_ofdm_get_status.argtypes = [C.c_void_p, C.c_int, C.POINTER(OfdmStatus)]
+    L.dabgpu_ofdm_pop_frames.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(FrameInfo), C.POINTER(C.c_int)]
+    L.dabgpu_ofdm_fetch_latest.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.dabgpu_viterbi_decode.argtypes = [C.c_void_p, C.POINTER(ViterbiJob), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.dabgpu_msc_configure.argtypes = [C.c_void_p, C.c_int, C.POINTER(SubchannelC), C.c_int]
+    L.dabgpu_softbits_push.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+    L.dabgpu_chan_decode.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.dabgpu_chan_get_status.argtypes = [C.c_void_p, C.c_int, C.POINTER(ChanStatus)]
+    L.dabgpu_chan_get_fic.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.dabgpu_chan_get_msc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int)]
+    L.dabgpu_chan_get_dabplus_events.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.dabgpu_rs_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.dabgpu_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != OK:
+        raise DabGpuError(rc, load_library().dabgpu_last_error().decode(errors="replace"))
+
+
+def get_params(mode: int) -> Params:
+    p = Params()
+    _check(load_library().dabgpu_get_params(mode, C.byref(p)))
+    return p
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+class DabGpu:
+    """One context = one GPU, `max_streams` independent IQ streams (mirrors Radio_Block x N)."""
+
+    def __init__(self, mode: int = 1, max_streams: int = 1, device: int = 0, iq_format: int = IQ_U8, ring_samples: int = 0,
+                 frame_slots: int = 0, max_subchannels: int = 0, cuda_stream: Optional[int] = None, ofdm_overrides: Optional[dict] = None):
+        self.L = load_library()
+        cfg = Config()
+        self.L.dabgpu_config_default(C.byref(cfg), mode)
+        cfg.device = device
+        cfg.max_streams = max_streams
+        cfg.iq_format = iq_format
+        cfg.ring_samples = ring_samples
+        cfg.frame_slots = frame_slots
+        cfg.max_subchannels = max_subchannels
+        cfg.cuda_stream = cuda_stream
+        for k, v in (ofdm_overrides or {}).items():
+            setattr(cfg.ofdm, k, v)
+        self.h = C.c_void_p()
+        _check(self.L.dabgpu_ctx_create(C.byref(cfg), C.byref(self.h)))
+        self.mode = mode
+        self.max_streams = max_streams
+        self.iq_format = iq_format
+        self.P = get_params(mode)
+        self._subs = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dabgpu_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _check(self.L.dabgpu_sync(self.h))
+
+    @property
+    def cuda_stream(self) -> int:
+        return int(self.L.dabgpu_cuda_stream(self.h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.dabgpu_launch_count(self.h))
+
+    # ---- Viterbi -------------------------------------------------------------------------
+    def viterbi_decode(self, soft_list: Sequence[np.ndarray], segments_list: Sequence[Sequence[Tuple[int, int]]],
+                       descramble: bool = False, n_out_bytes: Optional[Sequence[int]] = None):
+        """Batch of independent trellises.  Returns (list of byte arrays, path errors)."""
+        n = len(soft_list)
+        jobs = (ViterbiJob * n)()
+        soft_off, out_off = 0, 0
+        outs = []
+        for i, (soft, segs) in enumerate(zip(soft_list, segments_list)):
+            steps = sum(nb for _, nb in segs) // 4
+            nout = (steps - 6) // 8 if n_out_bytes is None else n_out_bytes[i]
+            j = jobs[i]
+            j.soft_offset, j.n_soft, j.n_seg = soft_off, soft.size, len(segs)
+            for k, (pi, nb) in enumerate(segs):
+                j.seg_pi[k] = pi
+                j.seg_bits[k] = nb
+            j.out_offset, j.n_out_bytes, j.descramble = out_off, nout, int(descramble)
+            soft_off += soft.size
+            outs.append((out_off, nout))
+            out_off += (nout + 15) & ~15
+        soft_all = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.int8) for s in soft_list]))
+        out = np.zeros(max(out_off, 16), dtype=np.uint8)
+        perr = np.zeros(n, dtype=np.uint64)
+        _check(self.L.dabgpu_viterbi_decode(self.h, jobs, n, _ptr(soft_all), soft_all.size, _ptr(out), out.size, _ptr(perr)))
+        return [out[o:o + m].copy() for o, m in outs], perr
+
+    # ---- channel decode ------------------------------------------------------------------
+    def msc_configure(self, stream: int, subs: Sequence) -> None:
+        arr = (SubchannelC * max(len(subs), 1))()
+        for i, s in enumerate(subs):
+            arr[i].start_address, arr[i].length = s.start_address, s.length
+            arr[i].is_uep, arr[i].uep_prot_index = int(s.is_uep), s.uep_index
+            arr[i].eep_prot_level, arr[i].eep_type_b = s.eep_level, int(s.eep_type_b)
+            arr[i].is_dabplus = int(getattr(s, "dabplus", False))
+        _check(self.L.dabgpu_msc_configure(self.h, stream, arr, len(subs)))
+        self._subs[stream] = list(subs)
+
+    def softbits_push(self, frames: np.ndarray, first_stream: int = 0) -> None:
+        """frames: [n_streams, nb_frame_bits] int8"""
+        frames = np.ascontiguousarray(frames, dtype=np.int8)
+        assert frames.ndim == 2 and frames.shape[1] == self.P.nb_frame_bits
+        _check(self.L.dabgpu_softbits_push(self.h, _ptr(frames), frames.shape[1], first_stream, frames.shape[0]))
+
+    def chan_decode(self, first_stream: int = 0, n_streams: Optional[int] = None) -> None:
+        _check(self.L.dabgpu_chan_decode(self.h, first_stream, self.max_streams - first_stream if n_streams is None else n_streams))
+
+    def chan_status(self, stream: int) -> Tuple[int, int]:
+        st = ChanStatus()
+        _check(self.L.dabgpu_chan_get_status(self.h, stream, C.byref(st)))
+        return st.decoded, st.frame_index
+
+    def get_fic(self, stream: int) -> Tuple[np.ndarray, np.ndarray]:
+        n = self.P.nb_cifs * self.P.nb_fibs_per_cif
+        fibs = np.zeros((n, 32), dtype=np.uint8)
+        ok = np.zeros(n, dtype=np.uint8)
+        _check(self.L.dabgpu_chan_get_fic(self.h, stream, _ptr(fibs), _ptr(ok)))
+        return fibs, ok
+
+    def get_msc(self, stream: int, sub_index: int) -> Tuple[np.ndarray, np.ndarray]:
+        nb = C.c_int(0)
+        _check(self.L.dabgpu_chan_get_msc(self.h, stream, sub_index, None, 0, None, C.byref(nb)))
+        out = np.zeros((self.P.nb_cifs, nb.value), dtype=np.uint8)
+        valid = np.zeros(self.P.nb_cifs, dtype=np.uint8)
+        _check(self.L.dabgpu_chan_get_msc(self.h, stream, sub_index, _ptr(out), out.size, _ptr(valid), C.byref(nb)))
+        return out, valid
+
+    def get_dabplus_events(self, stream: int, sub_index: int) -> bytes:
+        buf = np.zeros(1 << 16, dtype=np.uint8)
+        n = C.c_size_t(0)
+        _check(self.L.dabgpu_chan_get_dabplus_events(self.h, stream, sub_index, _ptr(buf), buf.size, C.byref(n)))
+        return buf[:n.value].tobytes()
+
+    def rs_decode(self, codewords: np.ndarray, nroots: int = 10, pad: int = 135):
+        cw = np.ascontiguousarray(codewords, dtype=np.uint8).copy()
+        assert cw.ndim == 2 and cw.shape[1] == 255 - pad
+        counts = np.zeros(cw.shape[0], dtype=np.int32)
+        pos = np.zeros((cw.shape[0], nroots), dtype=np.int32)
+        _check(self.L.dabgpu_rs_decode(self.h, _ptr(cw), cw.shape[0], nroots, pad, _ptr(counts), _ptr(pos)))
+        return counts, cw, pos
+
+    def counters(self) -> dict:
+        c = Counters()
+        _check(self.L.dabgpu_get_counters(self.h, C.byref(c)))
+        return {n: int(getattr(c, n)) for n, _ in Counters._fields_}
+
+    # ---- OFDM ----------------------------------------------------------------------------
+    def ofdm_reset(self, stream: int = -1):
+        _check(self.L.dabgpu_ofdm_reset(self.h, stream))
+
+    def ofdm_process(self, iq: np.ndarray, first_stream: int = 0, block_size: int = 65536):
+        """iq: [n_streams, n_samples*2] uint8 (IQ_U8) or [n_streams, n_samples] complex64 (IQ_C32), host memory."""
+        if self.iq_format == IQ_U8:
+            iq = np.ascontiguousarray(iq, dtype=np.uint8)
+            n_samples = iq.shape[1] // 2
+        else:
+            iq = np.ascontiguousarray(iq, dtype=np.complex64)
+            n_samples = iq.shape[1]
+        _check(self.L.dabgpu_ofdm_process(self.h, _ptr(iq), iq.strides[0], first_stream, iq.shape[0], n_samples, block_size))
+
+    def ofdm_attach_device_input(self, dev_ptr: int, stream_stride_samples: int, capacity_samples: int):
+        _check(self.L.dabgpu_ofdm_attach_device_input(self.h, C.c_void_p(dev_ptr), stream_stride_samples, capacity_samples))
+
+    def ofdm_advance(self, n_samples: int, block_size: int = 65536, first_stream: int = 0, n_streams: Optional[int] = None):
+        _check(self.L.dabgpu_ofdm_advance(self.h, first_stream, self.max_streams - first_stream if n_streams is None else n_streams,
+                                          n_samples, block_size))
+
+    def ofdm_status(self, stream: int) -> dict:
+        st = OfdmStatus()
+        _check(self.L.dabgpu_ofdm_get_status(self.h, stream, C.byref(st)))
+        return {n: getattr(st, n) for n, _ in OfdmStatus._fields_}
+
+    def ofdm_pop_frames(self, stream: int, max_frames: int = 64):
+        frames = np.zeros((max_frames, self.P.nb_frame_bits), dtype=np.int8)
+        infos = (FrameInfo * max_frames)()
+        n = C.c_int(0)
+        _check(self.L.dabgpu_ofdm_pop_frames(self.h, stream, _ptr(frames), max_frames, infos, C.byref(n)))
+        return [(frames[i].copy(), infos[i].freq_coarse_offset, infos[i].freq_fine_offset, infos[i].fine_time_offset) for i in range(n.value)]
+
+    def ofdm_fetch_latest(self, first_stream: int = 0, n_streams: Optional[int] = None):
+        n = self.max_streams - first_stream if n_streams is None else n_streams
+        frames = np.zeros((n, self.P.nb_frame_bits), dtype=np.int8)
+        produced = np.zeros(n, dtype=np.uint8)
+        _check(self.L.dabgpu_ofdm_fetch_latest(self.h, first_stream, n, _ptr(frames), _ptr(produced)))
+        return frames, produced

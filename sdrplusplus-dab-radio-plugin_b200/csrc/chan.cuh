@@ -1,0 +1,131 @@
+// chan.cuh -- channel decoding of whole transmission frames taken from the soft-bit frame ring:
+// FIC FIB groups and MSC sub-channels are turned into Viterbi jobs on the device.
+//   BasicRadio::Process split            basic_radio/basic_radio.cpp:41-65
+//   BasicFICRunner::Process              basic_radio/basic_fic_runner.cpp:34-49
+//   FIC_Decoder::DecodeFIBGroup          dab/fic/fic_decoder.cpp:53-117
+//   MSC_Decoder::DecodeCIF               dab/msc/msc_decoder.cpp:46-154
+//   CIF_Deinterleaver                    dab/msc/cif_deinterleaver.cpp:20-71  (fused into the Viterbi loader as a gather)
+#pragma once
+#include "viterbi.cuh"
+
+#define CIF_OUT_STRIDE 6912u     // decoded bytes per CIF can never exceed 55296/8
+#define FIC_GROUP_BYTES 128u     // 96 used in modes I/II/IV
+
+struct SubCfgDev {
+    uint32_t start_bit, nb_bits;
+    uint32_t seg_step_end[DABGPU_MAX_SEGMENTS];
+    uint32_t seg_in_base[DABGPU_MAX_SEGMENTS];
+    uint8_t seg_pi[8];
+    uint32_t n_seg, total_steps, n_out_bytes, out_offset;
+    uint32_t is_dabplus, pad0, pad1, pad2;
+};
+
+struct ChanDev {
+    // geometry
+    GatherGeom geom;
+    uint32_t nb_fibs_per_cif, fib_group_bits, fic_enabled;
+    uint32_t max_subs, jobs_per_stream;
+    // per-stream state / config
+    const int8_t* frames;            // [stream][slot][frame_bits]
+    size_t stream_frames_stride;     // slots*frame_bits
+    const uint32_t* frames_written;  // [stream]
+    uint32_t* frames_decoded;        // [stream]
+    const SubCfgDev* subcfg;         // [stream][max_subs]
+    const uint32_t* n_subs;          // [stream]
+    uint32_t* cifs_consumed;         // [stream][max_subs]
+    // outputs of the last decode
+    uint8_t* fic_out;                // [stream][nb_cifs][FIC_GROUP_BYTES]
+    uint8_t* fic_crc;                // [stream][nb_cifs][4]
+    uint8_t* msc_out;                // [stream][nb_cifs][CIF_OUT_STRIDE]
+    uint8_t* msc_valid;              // [stream][nb_cifs][max_subs]
+    int32_t* status;                 // [stream][2] = {decoded, frame_index}
+    unsigned long long* counters;    // see CNT_* below
+};
+
+enum { CNT_FRAMES_DEMOD = 0, CNT_FRAMES_CHAN, CNT_FIB_OK, CNT_FIB_TOTAL, CNT_MSC_BYTES, CNT_SF_OK, CNT_SF_RS_FAIL,
+       CNT_SF_FIRE_FAIL, CNT_AU_OK, CNT_AU_CRC_FAIL, CNT_COUNT };
+
+// One thread per potential job: (stream, j).  j < nb_cifs => FIB group j; otherwise sub-channel x CIF.
+__global__ void k_chan_build_jobs(const ChanDev C, VitJobDev* __restrict__ jobs, const int first_stream, const int n_streams) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = uint32_t(n_streams) * C.jobs_per_stream;
+    if (gid >= total) return;
+    const uint32_t si = gid / C.jobs_per_stream, j = gid - si * C.jobs_per_stream;
+    const uint32_t s = uint32_t(first_stream) + si;
+    VitJobDev J;
+    memset(&J, 0, sizeof(J));
+    const uint32_t t = C.frames_decoded[s];
+    const bool has_frame = C.frames_written[s] > t;
+    const uint32_t nb_cifs = C.geom.nb_cifs;
+    if (j == 0) {
+        C.status[2 * s + 0] = has_frame ? 1 : 0;
+        C.status[2 * s + 1] = int32_t(t);
+    }
+    if (has_frame) {
+        const int8_t* ring = C.frames + size_t(s) * C.stream_frames_stride;
+        if (j < nb_cifs) {
+            if (C.fic_enabled) {
+                // PI_16 x 21 blocks, PI_15 x 3 blocks, tail (fic_decoder.cpp:74-85)
+                J.src = ring + size_t(t & C.geom.slot_mask) * C.geom.frame_bits + size_t(j) * C.fib_group_bits;
+                J.out = C.fic_out + (size_t(s) * nb_cifs + j) * FIC_GROUP_BYTES;
+                J.crc_ok = C.fic_crc + (size_t(s) * nb_cifs + j) * 4u;
+                J.seg_pi[0] = 16; J.seg_pi[1] = 15; J.seg_pi[2] = 0;
+                J.seg_step_end[0] = 672; J.seg_step_end[1] = 768; J.seg_step_end[2] = 774;
+                J.seg_step_end[3] = 774; J.seg_step_end[4] = 774;
+                J.seg_in_base[0] = 0; J.seg_in_base[1] = 2016; J.seg_in_base[2] = 2292;
+                J.n_seg = 3; J.total_steps = 774; J.n_out_bytes = 96;
+                J.flags = VJ_DESCRAMBLE | VJ_FIB_CRC;
+                J.n_fibs = C.nb_fibs_per_cif;
+            }
+        } else {
+            const uint32_t jj = j - nb_cifs;
+            const uint32_t sub = jj / nb_cifs, c = jj - sub * nb_cifs;
+            if (sub < C.n_subs[s]) {
+                const SubCfgDev cfg = C.subcfg[size_t(s) * C.max_subs + sub];
+                // CIF_Deinterleaver::Deinterleave returns false until 16 CIFs were consumed (cif_deinterleaver.cpp:38-41)
+                const uint32_t consumed = C.cifs_consumed[size_t(s) * C.max_subs + sub] + c + 1u;
+                const bool valid = consumed >= 16u;
+                C.msc_valid[(size_t(s) * nb_cifs + c) * C.max_subs + sub] = valid ? 1 : 0;
+                if (valid) {
+                    J.src = ring;
+                    J.out = C.msc_out + (size_t(s) * nb_cifs + c) * CIF_OUT_STRIDE + cfg.out_offset;
+#pragma unroll
+                    for (int i = 0; i < DABGPU_MAX_SEGMENTS; i++) { J.seg_step_end[i] = cfg.seg_step_end[i]; J.seg_in_base[i] = cfg.seg_in_base[i]; }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) J.seg_pi[i] = cfg.seg_pi[i];
+                    J.n_seg = cfg.n_seg; J.total_steps = cfg.total_steps; J.n_out_bytes = cfg.n_out_bytes;
+                    J.flags = VJ_DESCRAMBLE | VJ_GATHER;
+                    J.newest_cif = t * nb_cifs + c;
+                    J.sub_start_bit = cfg.start_bit;
+                }
+            }
+        }
+    }
+    jobs[gid] = J;
+}
+
+// One thread per stream: advance the consumption counters after the Viterbi pass.
+__global__ void k_chan_finish(const ChanDev C, const int first_stream, const int n_streams) {
+    const uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= uint32_t(n_streams)) return;
+    const uint32_t s = uint32_t(first_stream) + si;
+    if (!C.status[2 * s]) return;
+    const uint32_t nb_cifs = C.geom.nb_cifs;
+    unsigned long long fib_ok = 0, bytes = 0;
+    if (C.fic_enabled) {
+        for (uint32_t c = 0; c < nb_cifs; c++)
+            for (uint32_t f = 0; f < C.nb_fibs_per_cif; f++) fib_ok += C.fic_crc[(size_t(s) * nb_cifs + c) * 4u + f];
+        atomicAdd(&C.counters[CNT_FIB_TOTAL], (unsigned long long)(nb_cifs * C.nb_fibs_per_cif));
+        atomicAdd(&C.counters[CNT_FIB_OK], fib_ok);
+    }
+    const uint32_t ns = C.n_subs[s];
+    for (uint32_t sub = 0; sub < ns; sub++) {
+        uint32_t& cc = C.cifs_consumed[size_t(s) * C.max_subs + sub];
+        for (uint32_t c = 0; c < nb_cifs; c++)
+            if (C.msc_valid[(size_t(s) * nb_cifs + c) * C.max_subs + sub]) bytes += C.subcfg[size_t(s) * C.max_subs + sub].n_out_bytes;
+        cc = min(cc + nb_cifs, 1u << 30);
+    }
+    atomicAdd(&C.counters[CNT_MSC_BYTES], bytes);
+    atomicAdd(&C.counters[CNT_FRAMES_CHAN], 1ull);
+    C.frames_decoded[s] += 1u;
+}

@@ -1,0 +1,597 @@
+// dabgpu.cu -- libdabgpu.so: C ABI (include/dabgpu.h) over the sm_100a kernels.  Unity build.
+#include "common.cuh"
+#include "tables.cuh"
+#include "viterbi.cuh"
+#include "chan.cuh"
+#include "dabplus.cuh"
+#include "ofdm.cuh"
+
+#define DABGPU_VERSION "dabgpu 0.1 (sm_100a)"
+
+struct SubHost {
+    dabgpu_subchannel sc;
+    Schedule sched;
+    uint32_t n_out_bytes, out_offset;
+};
+
+struct dabgpu_ctx {
+    dabgpu_config cfg;
+    dabgpu_params P;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 0;
+    uint64_t launches = 0;
+    int frame_slots = 0, max_subs = 0;
+
+    // Viterbi
+    DevBuf d_prbs, d_counter, d_scratch, d_jobs;
+    uint32_t scratch_steps = 0;
+    int vit_blocks = 0;
+    size_t prbs_words = 0;
+    DevBuf d_vsoft, d_vout, d_verr;   // staging of dabgpu_viterbi_decode
+
+    // soft-bit frame ring + channel decode state
+    DevBuf d_frames, d_frames_written, d_frames_decoded, d_frame_info;
+    DevBuf d_subcfg, d_nsubs, d_cifs_consumed;
+    DevBuf d_fic_out, d_fic_crc, d_msc_out, d_msc_valid, d_status, d_counters;
+    std::vector<std::vector<SubHost>> subs;
+    ChanDev chan;
+    PinnedBuf h_status, h_stage;
+    std::vector<uint32_t> h_frames_popped;   // per stream, host side cursor of dabgpu_ofdm_pop_frames
+
+    // DAB+ superframe stage
+    DabPlusState dabplus;
+
+    // OFDM
+    OfdmState ofdm;
+};
+
+static bool is_pow2(size_t v) { return v && !(v & (v - 1)); }
+
+extern "C" {
+
+const char* dabgpu_version(void) { return DABGPU_VERSION; }
+const char* dabgpu_last_error(void) { return g_last_error; }
+
+int dabgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void dabgpu_config_default(dabgpu_config* cfg, int transmission_mode) {
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->device = 0;
+    cfg->transmission_mode = transmission_mode;
+    cfg->max_streams = 1;
+    cfg->iq_format = DABGPU_IQ_U8;
+    cfg->ring_samples = 0;
+    cfg->frame_slots = 0;
+    cfg->max_subchannels = 0;
+    cfg->cuda_stream = nullptr;
+    // OFDM_Demod_Config defaults, ofdm/ofdm_demodulator.h:24-45
+    cfg->ofdm.signal_l1_update_beta = 0.95f;
+    cfg->ofdm.signal_l1_nb_samples = 100;
+    cfg->ofdm.signal_l1_nb_decimate = 5;
+    cfg->ofdm.null_thresh_start = 0.35f;
+    cfg->ofdm.null_thresh_end = 0.75f;
+    cfg->ofdm.fine_freq_update_beta = 0.9f;
+    cfg->ofdm.is_coarse_freq_correction = 1;
+    cfg->ofdm.max_coarse_freq_correction_norm = 0.5f;
+    cfg->ofdm.coarse_freq_slow_beta = 0.1f;
+    cfg->ofdm.impulse_peak_threshold_db = 20.0f;
+    cfg->ofdm.impulse_peak_distance_probability = 0.15f;
+}
+
+int dabgpu_get_params(int transmission_mode, dabgpu_params* out) {
+    if (!out) return set_error(DABGPU_ERR_INVALID, "null output");
+    return fill_params(transmission_mode, out);
+}
+
+static int ensure_scratch(dabgpu_ctx* ctx, uint32_t steps) {
+    if (steps <= ctx->scratch_steps) return DABGPU_OK;
+    const uint32_t rounded = (steps + 63u) & ~63u;
+    const size_t slots = size_t(ctx->vit_blocks) * VIT_WARPS_PER_BLOCK;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    int rc = ctx->d_scratch.alloc(slots * rounded * sizeof(uint2));
+    if (rc) return rc;
+    ctx->scratch_steps = rounded;
+    return DABGPU_OK;
+}
+
+int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
+    if (!cfg || !out) return set_error(DABGPU_ERR_INVALID, "null argument");
+    *out = nullptr;
+    dabgpu_params P;
+    int rc = fill_params(cfg->transmission_mode, &P);
+    if (rc) return rc;
+    if (cfg->max_streams < 1) return set_error(DABGPU_ERR_INVALID, "max_streams must be >= 1");
+    if (cfg->iq_format != DABGPU_IQ_U8 && cfg->iq_format != DABGPU_IQ_C32) return set_error(DABGPU_ERR_INVALID, "bad iq_format");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_error(DABGPU_ERR_CUDA, "no CUDA device available: libdabgpu has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return set_error(DABGPU_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return set_error(DABGPU_ERR_CUDA, "device %s is sm_%d%d; libdabgpu is built for sm_100a only", prop.name, prop.major, prop.minor);
+
+    dabgpu_ctx* ctx = new dabgpu_ctx();
+    ctx->cfg = *cfg;
+    ctx->P = P;
+    ctx->num_sms = prop.multiProcessorCount;
+    const int S = cfg->max_streams;
+    int min_slots = 8;
+    // the time de-interleaver needs 16 CIFs of history plus the frame being written
+    while (min_slots * P.nb_cifs < 16 + 2 * P.nb_cifs) min_slots *= 2;
+    ctx->frame_slots = cfg->frame_slots > 0 ? cfg->frame_slots : min_slots;
+    if (!is_pow2(size_t(ctx->frame_slots)) || ctx->frame_slots < min_slots) {
+        delete ctx;
+        return set_error(DABGPU_ERR_INVALID, "frame_slots must be a power of two >= %d", min_slots);
+    }
+    ctx->max_subs = cfg->max_subchannels > 0 ? cfg->max_subchannels : 64;
+    if (cfg->cuda_stream) {
+        ctx->stream = (cudaStream_t)cfg->cuda_stream;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete ctx; return set_error(DABGPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        ctx->own_stream = true;
+    }
+#define TRY_OR_FREE(expr) do { rc = (expr); if (rc) { dabgpu_ctx_destroy(ctx); return rc; } } while (0)
+    TRY_OR_FREE(upload_constant_tables());
+    {
+        std::vector<uint32_t> w;
+        ctx->prbs_words = 2048;   // 8192 bytes >= CIF_OUT_STRIDE
+        host_prbs_words(w, ctx->prbs_words);
+        TRY_OR_FREE(ctx->d_prbs.alloc(w.size() * 4));
+        cudaMemcpy(ctx->d_prbs.p, w.data(), w.size() * 4, cudaMemcpyHostToDevice);
+    }
+    TRY_OR_FREE(ctx->d_counter.alloc(64));
+    ctx->vit_blocks = ctx->num_sms * 8;
+    TRY_OR_FREE(ensure_scratch(ctx, 1600));
+
+    // frame ring + channel decode buffers
+    const size_t frame_bits = size_t(P.nb_frame_bits);
+    TRY_OR_FREE(ctx->d_frames.alloc(size_t(S) * ctx->frame_slots * frame_bits));
+    TRY_OR_FREE(ctx->d_frames_written.alloc(size_t(S) * 4));
+    TRY_OR_FREE(ctx->d_frames_decoded.alloc(size_t(S) * 4));
+    TRY_OR_FREE(ctx->d_frame_info.alloc(size_t(S) * ctx->frame_slots * sizeof(dabgpu_frame_info)));
+    TRY_OR_FREE(ctx->d_subcfg.alloc(size_t(S) * ctx->max_subs * sizeof(SubCfgDev)));
+    TRY_OR_FREE(ctx->d_nsubs.alloc(size_t(S) * 4));
+    TRY_OR_FREE(ctx->d_cifs_consumed.alloc(size_t(S) * ctx->max_subs * 4));
+    TRY_OR_FREE(ctx->d_fic_out.alloc(size_t(S) * P.nb_cifs * FIC_GROUP_BYTES));
+    TRY_OR_FREE(ctx->d_fic_crc.alloc(size_t(S) * P.nb_cifs * 4));
+    TRY_OR_FREE(ctx->d_msc_out.alloc(size_t(S) * P.nb_cifs * CIF_OUT_STRIDE));
+    TRY_OR_FREE(ctx->d_msc_valid.alloc(size_t(S) * P.nb_cifs * ctx->max_subs));
+    TRY_OR_FREE(ctx->d_status.alloc(size_t(S) * 8));
+    TRY_OR_FREE(ctx->d_counters.alloc(CNT_COUNT * 8));
+    TRY_OR_FREE(ctx->h_status.alloc(size_t(S) * 8 + 4096));
+    cudaMemset(ctx->d_frames.p, 0, ctx->d_frames.bytes);
+    cudaMemset(ctx->d_frames_written.p, 0, ctx->d_frames_written.bytes);
+    cudaMemset(ctx->d_frames_decoded.p, 0, ctx->d_frames_decoded.bytes);
+    cudaMemset(ctx->d_frame_info.p, 0, ctx->d_frame_info.bytes);
+    cudaMemset(ctx->d_subcfg.p, 0, ctx->d_subcfg.bytes);
+    cudaMemset(ctx->d_nsubs.p, 0, ctx->d_nsubs.bytes);
+    cudaMemset(ctx->d_cifs_consumed.p, 0, ctx->d_cifs_consumed.bytes);
+    cudaMemset(ctx->d_fic_out.p, 0, ctx->d_fic_out.bytes);
+    cudaMemset(ctx->d_fic_crc.p, 0, ctx->d_fic_crc.bytes);
+    cudaMemset(ctx->d_msc_out.p, 0, ctx->d_msc_out.bytes);
+    cudaMemset(ctx->d_msc_valid.p, 0, ctx->d_msc_valid.bytes);
+    cudaMemset(ctx->d_status.p, 0, ctx->d_status.bytes);
+    cudaMemset(ctx->d_counters.p, 0, ctx->d_counters.bytes);
+    ctx->subs.resize(size_t(S));
+    ctx->h_frames_popped.assign(size_t(S), 0);
+
+    ChanDev& C = ctx->chan;
+    C.geom.nb_cifs = uint32_t(P.nb_cifs);
+    C.geom.frame_bits = uint32_t(P.nb_frame_bits);
+    C.geom.fic_bits = uint32_t(P.nb_fic_bits);
+    C.geom.cif_bits = uint32_t(P.nb_cif_bits);
+    C.geom.slot_mask = uint32_t(ctx->frame_slots - 1);
+    C.nb_fibs_per_cif = uint32_t(P.nb_fibs_per_cif);
+    C.fib_group_bits = uint32_t(P.nb_fib_group_bits);
+    // FIC_Decoder only decodes 2304-bit FIB groups (fic_decoder.cpp:66-72): mode III is skipped like the reference
+    C.fic_enabled = (P.nb_fib_group_bits == 2304) ? 1u : 0u;
+    C.max_subs = uint32_t(ctx->max_subs);
+    C.jobs_per_stream = uint32_t(P.nb_cifs) * (1u + uint32_t(ctx->max_subs));
+    C.frames = ctx->d_frames.as<int8_t>();
+    C.stream_frames_stride = size_t(ctx->frame_slots) * frame_bits;
+    C.frames_written = ctx->d_frames_written.as<uint32_t>();
+    C.frames_decoded = ctx->d_frames_decoded.as<uint32_t>();
+    C.subcfg = ctx->d_subcfg.as<SubCfgDev>();
+    C.n_subs = ctx->d_nsubs.as<uint32_t>();
+    C.cifs_consumed = ctx->d_cifs_consumed.as<uint32_t>();
+    C.fic_out = ctx->d_fic_out.as<uint8_t>();
+    C.fic_crc = ctx->d_fic_crc.as<uint8_t>();
+    C.msc_out = ctx->d_msc_out.as<uint8_t>();
+    C.msc_valid = ctx->d_msc_valid.as<uint8_t>();
+    C.status = ctx->d_status.as<int32_t>();
+    C.counters = ctx->d_counters.as<unsigned long long>();
+
+    TRY_OR_FREE(dabplus_init(ctx->dabplus, S, ctx->max_subs, P.nb_cifs));
+    TRY_OR_FREE(ofdm_init(ctx->ofdm, ctx->cfg, P, ctx->frame_slots, ctx->d_frames.as<int8_t>(), ctx->d_frames_written.as<uint32_t>(),
+                          ctx->d_frame_info.as<dabgpu_frame_info>(), ctx->d_counters.as<unsigned long long>()));
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { dabgpu_ctx_destroy(ctx); return set_error(DABGPU_ERR_CUDA, "context initialisation: %s", cudaGetErrorString(e)); }
+    *out = ctx;
+    return DABGPU_OK;
+}
+
+void dabgpu_ctx_destroy(dabgpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ofdm_destroy(ctx->ofdm);
+    dabplus_destroy(ctx->dabplus);
+    DevBuf* bufs[] = {&ctx->d_prbs, &ctx->d_counter, &ctx->d_scratch, &ctx->d_jobs, &ctx->d_vsoft, &ctx->d_vout, &ctx->d_verr,
+                      &ctx->d_frames, &ctx->d_frames_written, &ctx->d_frames_decoded, &ctx->d_frame_info, &ctx->d_subcfg, &ctx->d_nsubs,
+                      &ctx->d_cifs_consumed, &ctx->d_fic_out, &ctx->d_fic_crc, &ctx->d_msc_out, &ctx->d_msc_valid, &ctx->d_status,
+                      &ctx->d_counters};
+    for (DevBuf* b : bufs) b->release();
+    ctx->h_status.release();
+    ctx->h_stage.release();
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int dabgpu_sync(dabgpu_ctx* ctx) {
+    if (!ctx) return set_error(DABGPU_ERR_INVALID, "null context");
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DABGPU_OK;
+}
+
+void* dabgpu_cuda_stream(dabgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t dabgpu_launch_count(const dabgpu_ctx* ctx) { return ctx ? ctx->launches + ctx->ofdm.launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// Viterbi
+// ---------------------------------------------------------------------------------------------
+static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs) {
+    CUDA_TRY(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
+    const int blocks = ctx->vit_blocks;
+    k_viterbi<<<blocks, VIT_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(d_jobs, n_jobs, ctx->d_counter.as<int>(), ctx->d_scratch.as<uint2>(),
+                                                                     ctx->scratch_steps, ctx->d_prbs.as<uint32_t>(), ctx->chan.geom);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return DABGPU_OK;
+}
+
+int dabgpu_viterbi_decode(dabgpu_ctx* ctx, const dabgpu_viterbi_job* jobs, int n_jobs, const int8_t* soft_host, size_t soft_bytes,
+                          uint8_t* out_host, size_t out_bytes, uint64_t* path_error_host) {
+    if (!ctx || !jobs || !soft_host || !out_host) return set_error(DABGPU_ERR_INVALID, "null argument");
+    if (n_jobs <= 0) return DABGPU_OK;
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc;
+    if ((rc = ctx->d_vsoft.alloc(soft_bytes + 16))) return rc;
+    if ((rc = ctx->d_vout.alloc(out_bytes + 16))) return rc;
+    if ((rc = ctx->d_verr.alloc(size_t(n_jobs) * 8))) return rc;
+    if ((rc = ctx->d_jobs.alloc(size_t(n_jobs) * sizeof(VitJobDev)))) return rc;
+    std::vector<VitJobDev> hj(static_cast<size_t>(n_jobs));
+    uint32_t max_steps = 0;
+    for (int i = 0; i < n_jobs; i++) {
+        const dabgpu_viterbi_job& j = jobs[i];
+        VitJobDev& J = hj[size_t(i)];
+        memset(&J, 0, sizeof(J));
+        if (j.n_seg < 1 || j.n_seg > DABGPU_MAX_SEGMENTS) return set_error(DABGPU_ERR_INVALID, "job %d: n_seg %u out of range", i, j.n_seg);
+        uint32_t steps = 0, in_base = 0;
+        for (uint32_t k = 0; k < DABGPU_MAX_SEGMENTS; k++) {
+            if (k < j.n_seg) {
+                if (j.seg_pi[k] > 24) return set_error(DABGPU_ERR_INVALID, "job %d: puncture code %u out of range", i, j.seg_pi[k]);
+                if (j.seg_bits[k] % 4 != 0) return set_error(DABGPU_ERR_INVALID, "job %d: segment bits must be a multiple of the code rate", i);
+                J.seg_pi[k] = j.seg_pi[k];
+                J.seg_in_base[k] = in_base;
+                int c[8];
+                host_pi_counts(j.seg_pi[k], c);
+                const uint32_t groups = j.seg_bits[k] / 4;
+                uint32_t per8 = 0;
+                for (int g = 0; g < 8; g++) per8 += uint32_t(c[g]);
+                in_base += (groups / 8) * per8;
+                for (uint32_t g = 0; g < groups % 8; g++) in_base += uint32_t(c[g]);
+                steps += groups;
+            }
+            J.seg_step_end[k] = steps;
+        }
+        if (in_base > j.n_soft) return set_error(DABGPU_ERR_INVALID, "job %d: needs %u punctured symbols, only %u given", i, in_base, j.n_soft);
+        if (j.soft_offset + j.n_soft > soft_bytes) return set_error(DABGPU_ERR_INVALID, "job %d: soft range exceeds buffer", i);
+        if (size_t(j.n_out_bytes) * 8 + 6 > steps) return set_error(DABGPU_ERR_INVALID, "job %d: chainback of %u bytes exceeds %u decoded steps", i, j.n_out_bytes, steps);
+        if (j.out_offset + j.n_out_bytes > out_bytes) return set_error(DABGPU_ERR_INVALID, "job %d: output range exceeds buffer", i);
+        if (j.descramble && (j.n_out_bytes + 3) / 4 > ctx->prbs_words) return set_error(DABGPU_ERR_INVALID, "job %d: too long for the PRBS table", i);
+        J.n_seg = j.n_seg;
+        J.total_steps = steps;
+        J.n_out_bytes = j.n_out_bytes;
+        J.flags = j.descramble ? VJ_DESCRAMBLE : 0u;
+        J.src = ctx->d_vsoft.as<int8_t>() + j.soft_offset;
+        J.out = ctx->d_vout.as<uint8_t>() + j.out_offset;
+        J.path_error = ctx->d_verr.as<unsigned long long>() + i;
+        if (steps > max_steps) max_steps = steps;
+    }
+    if ((rc = ensure_scratch(ctx, max_steps))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_vsoft.p, soft_host, soft_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_jobs.p, hj.data(), hj.size() * sizeof(VitJobDev), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_vout.p, 0, out_bytes, ctx->stream));
+    if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), n_jobs))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_vout.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (path_error_host) CUDA_TRY(cudaMemcpyAsync(path_error_host, ctx->d_verr.p, size_t(n_jobs) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DABGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Channel decode of frames
+// ---------------------------------------------------------------------------------------------
+static int check_stream_range(dabgpu_ctx* ctx, int first, int n) {
+    if (!ctx) return set_error(DABGPU_ERR_INVALID, "null context");
+    if (first < 0 || n < 0 || first + n > ctx->cfg.max_streams) return set_error(DABGPU_ERR_INVALID, "stream range [%d,%d) outside [0,%d)", first, first + n, ctx->cfg.max_streams);
+    return DABGPU_OK;
+}
+
+int dabgpu_msc_configure(dabgpu_ctx* ctx, int stream, const dabgpu_subchannel* subs, int n_subs) {
+    int rc = check_stream_range(ctx, stream, 1);
+    if (rc) return rc;
+    if (n_subs < 0 || n_subs > ctx->max_subs) return set_error(DABGPU_ERR_INVALID, "n_subs %d exceeds max_subchannels %d", n_subs, ctx->max_subs);
+    if (n_subs > 0 && !subs) return set_error(DABGPU_ERR_INVALID, "null sub-channel table");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    std::vector<SubHost> hs;
+    std::vector<SubCfgDev> dev(static_cast<size_t>(ctx->max_subs));
+    memset(dev.data(), 0, dev.size() * sizeof(SubCfgDev));
+    uint32_t out_off = 0, max_steps = 0;
+    for (int i = 0; i < n_subs; i++) {
+        SubHost h;
+        h.sc = subs[i];
+        if (h.sc.start_address < 0 || h.sc.length <= 0 || (h.sc.start_address + h.sc.length) * 64 > ctx->P.nb_cif_bits)
+            return set_error(DABGPU_ERR_INVALID, "Subchannel bits %d:%d overflows MSC channel with %d bits", h.sc.start_address * 64,
+                             (h.sc.start_address + h.sc.length) * 64, ctx->P.nb_cif_bits);
+        if ((rc = make_schedule(h.sc, &h.sched))) return rc;
+        const int steps = h.sched.total_steps();
+        if (h.sched.punctured_bits() > h.sc.length * 64)
+            return set_error(DABGPU_ERR_INVALID, "sub-channel %d: protection profile needs %d soft bits, sub-channel has %d", i, h.sched.punctured_bits(), h.sc.length * 64);
+        h.n_out_bytes = uint32_t((steps - 6) / 8);
+        h.out_offset = out_off;
+        out_off += (h.n_out_bytes + 15u) & ~15u;
+        if (out_off > CIF_OUT_STRIDE) return set_error(DABGPU_ERR_OVERFLOW, "decoded bytes per CIF exceed %u", CIF_OUT_STRIDE);
+        SubCfgDev& d = dev[size_t(i)];
+        d.start_bit = uint32_t(h.sc.start_address * 64);
+        d.nb_bits = uint32_t(h.sc.length * 64);
+        uint32_t st = 0, inb = 0;
+        for (int k = 0; k < DABGPU_MAX_SEGMENTS; k++) {
+            if (k < h.sched.n_seg) {
+                d.seg_pi[k] = uint8_t(h.sched.pi[k]);
+                d.seg_in_base[k] = inb;
+                int c[8];
+                host_pi_counts(h.sched.pi[k], c);
+                const uint32_t groups = uint32_t(h.sched.bits[k] / 4);
+                uint32_t per8 = 0;
+                for (int g = 0; g < 8; g++) per8 += uint32_t(c[g]);
+                inb += (groups / 8) * per8;
+                for (uint32_t g = 0; g < groups % 8; g++) inb += uint32_t(c[g]);
+                st += groups;
+            }
+            d.seg_step_end[k] = st;
+        }
+        d.n_seg = uint32_t(h.sched.n_seg);
+        d.total_steps = uint32_t(steps);
+        d.n_out_bytes = h.n_out_bytes;
+        d.out_offset = h.out_offset;
+        d.is_dabplus = h.sc.is_dabplus ? 1u : 0u;
+        if (d.total_steps > max_steps) max_steps = d.total_steps;
+        hs.push_back(h);
+    }
+    if ((rc = ensure_scratch(ctx, max_steps))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpy(ctx->d_subcfg.as<SubCfgDev>() + size_t(stream) * ctx->max_subs, dev.data(), dev.size() * sizeof(SubCfgDev), cudaMemcpyHostToDevice));
+    const uint32_t ns = uint32_t(n_subs);
+    CUDA_TRY(cudaMemcpy(ctx->d_nsubs.as<uint32_t>() + stream, &ns, 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(ctx->d_cifs_consumed.as<uint32_t>() + size_t(stream) * ctx->max_subs, 0, size_t(ctx->max_subs) * 4));
+    if ((rc = dabplus_reset_stream(ctx->dabplus, stream))) return rc;
+    ctx->subs[size_t(stream)] = hs;
+    return DABGPU_OK;
+}
+
+int dabgpu_softbits_push(dabgpu_ctx* ctx, const int8_t* frames_host, size_t stride, int first, int n) {
+    int rc = check_stream_range(ctx, first, n);
+    if (rc) return rc;
+    if (!frames_host) return set_error(DABGPU_ERR_INVALID, "null frames");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    // BasicRadio::Process requires exactly nb_frame_bits per call (basic_radio.cpp:41-46): the caller passes whole frames
+    const size_t fb = size_t(ctx->P.nb_frame_bits);
+    if ((rc = ctx->h_stage.alloc(size_t(n) * 4 + 64))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint32_t* written = ctx->h_stage.as<uint32_t>();
+    CUDA_TRY(cudaMemcpy(written, ctx->d_frames_written.as<uint32_t>() + first, size_t(n) * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+        const size_t slot = written[i] & uint32_t(ctx->frame_slots - 1);
+        int8_t* dst = ctx->d_frames.as<int8_t>() + (size_t(first + i) * ctx->frame_slots + slot) * fb;
+        CUDA_TRY(cudaMemcpyAsync(dst, frames_host + size_t(i) * stride, fb, cudaMemcpyHostToDevice, ctx->stream));
+        written[i] += 1;
+    }
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_frames_written.as<uint32_t>() + first, written, size_t(n) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DABGPU_OK;
+}
+
+int dabgpu_chan_decode(dabgpu_ctx* ctx, int first, int n) {
+    int rc = check_stream_range(ctx, first, n);
+    if (rc) return rc;
+    if (n == 0) return DABGPU_OK;
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    const uint32_t total = uint32_t(n) * ctx->chan.jobs_per_stream;
+    if ((rc = ctx->d_jobs.alloc(size_t(total) * sizeof(VitJobDev)))) return rc;
+    k_chan_build_jobs<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->chan, ctx->d_jobs.as<VitJobDev>(), first, n);
+    ctx->launches++;
+    if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), int(total)))) return rc;
+    if ((rc = dabplus_run(ctx->dabplus, ctx->chan, first, n, ctx->stream, &ctx->launches))) return rc;
+    k_chan_finish<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->chan, first, n);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return DABGPU_OK;
+}
+
+int dabgpu_chan_get_status(dabgpu_ctx* ctx, int stream, dabgpu_chan_status* out) {
+    int rc = check_stream_range(ctx, stream, 1);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    int32_t st[2];
+    CUDA_TRY(cudaMemcpy(st, ctx->d_status.as<int32_t>() + 2 * stream, 8, cudaMemcpyDeviceToHost));
+    out->decoded = st[0];
+    out->frame_index = st[1];
+    return DABGPU_OK;
+}
+
+int dabgpu_chan_get_fic(dabgpu_ctx* ctx, int stream, uint8_t* fibs_host, uint8_t* crc_ok) {
+    int rc = check_stream_range(ctx, stream, 1);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const int nb_cifs = ctx->P.nb_cifs, nf = ctx->P.nb_fibs_per_cif;
+    std::vector<uint8_t> tmp(size_t(nb_cifs) * FIC_GROUP_BYTES), crc(size_t(nb_cifs) * 4);
+    CUDA_TRY(cudaMemcpy(tmp.data(), ctx->d_fic_out.as<uint8_t>() + size_t(stream) * nb_cifs * FIC_GROUP_BYTES, tmp.size(), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(crc.data(), ctx->d_fic_crc.as<uint8_t>() + size_t(stream) * nb_cifs * 4, crc.size(), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < nb_cifs; c++) {
+        if (fibs_host) memcpy(fibs_host + size_t(c) * nf * 32, tmp.data() + size_t(c) * FIC_GROUP_BYTES, size_t(nf) * 32);
+        if (crc_ok) for (int f = 0; f < nf; f++) crc_ok[c * nf + f] = ctx->chan.fic_enabled ? crc[size_t(c) * 4 + f] : 0;
+    }
+    return DABGPU_OK;
+}
+
+int dabgpu_chan_get_msc(dabgpu_ctx* ctx, int stream, int sub_index, uint8_t* out_host, size_t out_cap, uint8_t* valid, int* bytes_per_cif) {
+    int rc = check_stream_range(ctx, stream, 1);
+    if (rc) return rc;
+    const auto& hs = ctx->subs[size_t(stream)];
+    if (sub_index < 0 || size_t(sub_index) >= hs.size()) return set_error(DABGPU_ERR_INVALID, "sub-channel index %d not configured", sub_index);
+    const SubHost& h = hs[size_t(sub_index)];
+    const int nb_cifs = ctx->P.nb_cifs;
+    if (bytes_per_cif) *bytes_per_cif = int(h.n_out_bytes);
+    if (out_host && out_cap < size_t(nb_cifs) * h.n_out_bytes) return set_error(DABGPU_ERR_OVERFLOW, "output buffer too small");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < nb_cifs; c++) {
+        if (out_host)
+            CUDA_TRY(cudaMemcpy(out_host + size_t(c) * h.n_out_bytes,
+                                ctx->d_msc_out.as<uint8_t>() + (size_t(stream) * nb_cifs + c) * CIF_OUT_STRIDE + h.out_offset, h.n_out_bytes,
+                                cudaMemcpyDeviceToHost));
+        if (valid)
+            CUDA_TRY(cudaMemcpy(valid + c, ctx->d_msc_valid.as<uint8_t>() + (size_t(stream) * nb_cifs + c) * ctx->max_subs + sub_index, 1,
+                                cudaMemcpyDeviceToHost));
+    }
+    return DABGPU_OK;
+}
+
+int dabgpu_chan_get_dabplus_events(dabgpu_ctx* ctx, int stream, int sub_index, uint8_t* log_host, size_t log_cap, size_t* log_bytes) {
+    int rc = check_stream_range(ctx, stream, 1);
+    if (rc) return rc;
+    if (sub_index < 0 || size_t(sub_index) >= ctx->subs[size_t(stream)].size()) return set_error(DABGPU_ERR_INVALID, "sub-channel index %d not configured", sub_index);
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return dabplus_get_events(ctx->dabplus, stream, sub_index, log_host, log_cap, log_bytes);
+}
+
+int dabgpu_rs_decode(dabgpu_ctx* ctx, uint8_t* codewords_host, int n_codewords, int nroots, int pad, int* counts_host, int* positions_host) {
+    if (!ctx || !codewords_host || !counts_host) return set_error(DABGPU_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    return dabplus_rs_decode_batch(ctx->dabplus, codewords_host, n_codewords, nroots, pad, counts_host, positions_host, ctx->stream, &ctx->launches);
+}
+
+int dabgpu_get_counters(dabgpu_ctx* ctx, dabgpu_counters* out) {
+    if (!ctx || !out) return set_error(DABGPU_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    unsigned long long c[CNT_COUNT];
+    CUDA_TRY(cudaMemcpy(c, ctx->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+    out->frames_demodulated = c[CNT_FRAMES_DEMOD];
+    out->frames_channel_decoded = c[CNT_FRAMES_CHAN];
+    out->fibs_crc_ok = c[CNT_FIB_OK];
+    out->fibs_total = c[CNT_FIB_TOTAL];
+    out->msc_bytes_decoded = c[CNT_MSC_BYTES];
+    out->superframes_ok = c[CNT_SF_OK];
+    out->superframes_rs_fail = c[CNT_SF_RS_FAIL];
+    out->superframes_firecode_fail = c[CNT_SF_FIRE_FAIL];
+    out->au_ok = c[CNT_AU_OK];
+    out->au_crc_fail = c[CNT_AU_CRC_FAIL];
+    return DABGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// OFDM (implementation in ofdm.cuh)
+// ---------------------------------------------------------------------------------------------
+int dabgpu_ofdm_reset(dabgpu_ctx* ctx, int stream) {
+    if (!ctx) return set_error(DABGPU_ERR_INVALID, "null context");
+    if (stream < -1 || stream >= ctx->cfg.max_streams) return set_error(DABGPU_ERR_INVALID, "stream %d out of range", stream);
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    return ofdm_reset(ctx->ofdm, stream, ctx->stream);
+}
+
+int dabgpu_ofdm_process(dabgpu_ctx* ctx, const void* iq_host, size_t stride_bytes, int first, int n, int n_samples, int block_size) {
+    int rc = check_stream_range(ctx, first, n);
+    if (rc) return rc;
+    if (!iq_host || n_samples < 0) return set_error(DABGPU_ERR_INVALID, "bad IQ buffer");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    return ofdm_process(ctx->ofdm, iq_host, stride_bytes, first, n, n_samples, block_size, ctx->stream);
+}
+
+int dabgpu_ofdm_attach_device_input(dabgpu_ctx* ctx, const void* d_iq, size_t stride_samples, size_t capacity) {
+    if (!ctx || !d_iq) return set_error(DABGPU_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    return ofdm_attach(ctx->ofdm, d_iq, stride_samples, capacity, ctx->stream);
+}
+
+int dabgpu_ofdm_advance(dabgpu_ctx* ctx, int first, int n, int n_samples, int block_size) {
+    int rc = check_stream_range(ctx, first, n);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    return ofdm_advance(ctx->ofdm, first, n, n_samples, block_size, ctx->stream);
+}
+
+int dabgpu_ofdm_get_status(dabgpu_ctx* ctx, int stream, dabgpu_ofdm_status* out) {
+    int rc = check_stream_range(ctx, stream, 1);
+    if (rc) return rc;
+    if (!out) return set_error(DABGPU_ERR_INVALID, "null output");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    rc = ofdm_get_status(ctx->ofdm, stream, out, ctx->stream);
+    if (rc) return rc;
+    uint32_t written = 0;
+    CUDA_TRY(cudaMemcpy(&written, ctx->d_frames_written.as<uint32_t>() + stream, 4, cudaMemcpyDeviceToHost));
+    out->frames_queued = int(written - ctx->h_frames_popped[size_t(stream)]);
+    return DABGPU_OK;
+}
+
+int dabgpu_ofdm_pop_frames(dabgpu_ctx* ctx, int stream, int8_t* frames_host, int max_frames, dabgpu_frame_info* infos, int* n_out) {
+    int rc = check_stream_range(ctx, stream, 1);
+    if (rc) return rc;
+    if (!n_out) return set_error(DABGPU_ERR_INVALID, "null output");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint32_t written = 0;
+    CUDA_TRY(cudaMemcpy(&written, ctx->d_frames_written.as<uint32_t>() + stream, 4, cudaMemcpyDeviceToHost));
+    uint32_t& popped = ctx->h_frames_popped[size_t(stream)];
+    // frames older than the ring depth were overwritten: the observer model of the reference drops nothing, so
+    // callers must pop at least every frame_slots-2 frames; report the overrun instead of returning stale data
+    if (written - popped > uint32_t(ctx->frame_slots - 1)) {
+        popped = written - uint32_t(ctx->frame_slots - 1);
+    }
+    const size_t fb = size_t(ctx->P.nb_frame_bits);
+    int n = 0;
+    while (popped < written && n < max_frames) {
+        const size_t slot = popped & uint32_t(ctx->frame_slots - 1);
+        if (frames_host)
+            CUDA_TRY(cudaMemcpy(frames_host + size_t(n) * fb, ctx->d_frames.as<int8_t>() + (size_t(stream) * ctx->frame_slots + slot) * fb, fb, cudaMemcpyDeviceToHost));
+        if (infos)
+            CUDA_TRY(cudaMemcpy(infos + n, ctx->d_frame_info.as<dabgpu_frame_info>() + size_t(stream) * ctx->frame_slots + slot, sizeof(dabgpu_frame_info), cudaMemcpyDeviceToHost));
+        popped++;
+        n++;
+    }
+    *n_out = n;
+    return DABGPU_OK;
+}
+
+int dabgpu_ofdm_fetch_latest(dabgpu_ctx* ctx, int first, int n, int8_t* frames_host, uint8_t* produced) {
+    int rc = check_stream_range(ctx, first, n);
+    if (rc) return rc;
+    if (!frames_host || !produced) return set_error(DABGPU_ERR_INVALID, "null output");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    return ofdm_fetch_latest(ctx->ofdm, first, n, frames_host, produced, ctx->stream);
+}
+
+}  // extern "C"

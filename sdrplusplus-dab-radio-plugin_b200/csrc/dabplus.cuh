@@ -1,0 +1,425 @@
+// dabplus.cuh -- DAB+ audio superframe stage and Reed-Solomon decoder.
+//   AAC_Frame_Processor::{Process,CalculateFirecode,AccumulateFrame,ProcessSuperFrame,ReedSolomonDecode}
+//       dab/audio/aac_frame_processor.cpp:126-362
+//   Reed_Solomon_Decoder::Decode -> decode_rs_char   dab/algorithms/reed_solomon_decoder.cpp:192-477
+//       GF(2^8) poly 0x11D, fcr 0, prim 1; DAB+ uses 10 roots, pad 135 (aac_frame_processor.cpp:105-111)
+//
+// One warp per (stream, sub-channel): the per-sub-channel state machine is sequential over the CIFs of
+// a frame, the RS codewords of a superframe are decoded one per lane (codeword i = bytes {i + j*N}, so
+// lanes read consecutive bytes), corrections are applied in codeword order so the reference's
+// "stop at the first uncorrectable codeword" behaviour is preserved.
+#pragma once
+#include "chan.cuh"
+
+#define RS_MAX_ROOTS 32
+#define DP_MAX_EVENTS 16
+
+struct DabPlusSubState { int32_t collect, curr_frame, prev_nb, synced, desync, pad0, pad1, pad2; };
+struct DabPlusEvent { int32_t type, a, b, c, d, payload_off, payload_len, pad; };
+
+struct DabPlusDev {
+    DabPlusSubState* st;     // [stream][max_subs]
+    uint8_t* sf;             // [stream][5*CIF_OUT_STRIDE], sub-channel at 5*out_offset: accumulator of the 5 logical frames
+    uint8_t* sf_out;         // same layout: last completed (RS corrected, fire code valid) superframe, what the observers see
+    DabPlusEvent* events;    // [stream][max_subs][DP_MAX_EVENTS]
+    int32_t* n_events;       // [stream][max_subs]
+};
+
+struct DabPlusState {
+    DevBuf d_st, d_sf, d_sf_out, d_events, d_nevents, d_rs_cw, d_rs_cnt, d_rs_pos;
+    DabPlusDev dev;
+    int max_streams = 0, max_subs = 0, nb_cifs = 0;
+};
+
+struct GfTables { const uint8_t* ex; const uint8_t* lg; };
+
+__device__ __forceinline__ int gf_mod255(int x) {
+    while (x >= 255) { x -= 255; x = (x >> 8) + (x & 255); }
+    return x;
+}
+__device__ __forceinline__ uint8_t gf_mul_dev(const GfTables& T, uint8_t a, uint8_t b) {
+    return (a && b) ? T.ex[T.lg[a] + T.lg[b]] : uint8_t(0);
+}
+
+// Syndromes S_i = data(alpha^i), Horner from data[0] (reed_solomon_decoder.cpp:232-245).  Returns OR of all S_i.
+__device__ int rs_syndromes(const GfTables& T, const uint8_t* data, int stride, int n, int nroots, uint8_t* S) {
+    for (int i = 0; i < nroots; i++) S[i] = data[0];
+    for (int j = 1; j < n; j++) {
+        const uint8_t d = data[size_t(j) * stride];
+        for (int i = 0; i < nroots; i++) S[i] = uint8_t(d ^ (S[i] ? T.ex[gf_mod255(T.lg[S[i]] + i)] : 0));
+    }
+    int any = 0;
+    for (int i = 0; i < nroots; i++) any |= S[i];
+    return any;
+}
+
+// Berlekamp-Massey + Chien + Forney for fcr = 0, prim = 1 (reed_solomon_decoder.cpp:263-466).
+// Outputs error locations (incl. pad) and the value to XOR at each location; apply[j] = 0 where the
+// reference leaves the data untouched (zero error value or location inside the padding).
+__device__ int rs_solve(const GfTables& T, const uint8_t* S, int nroots, int pad, uint8_t* loc, uint8_t* xorval, uint8_t* apply) {
+    uint8_t lambda[RS_MAX_ROOTS + 1], b[RS_MAX_ROOTS + 1], t[RS_MAX_ROOTS + 1], omega[RS_MAX_ROOTS + 1], root[RS_MAX_ROOTS];
+    for (int i = 0; i <= nroots; i++) { lambda[i] = 0; b[i] = 0; }
+    lambda[0] = 1; b[0] = 1;
+    int el = 0;
+    for (int r = 1; r <= nroots; r++) {
+        uint8_t discr = 0;
+        for (int i = 0; i < r; i++) discr ^= gf_mul_dev(T, lambda[i], S[r - i - 1]);
+        if (discr == 0) {
+            for (int i = nroots; i > 0; i--) b[i] = b[i - 1];
+            b[0] = 0;
+        } else {
+            t[0] = lambda[0];
+            for (int i = 0; i < nroots; i++) t[i + 1] = uint8_t(lambda[i + 1] ^ gf_mul_dev(T, discr, b[i]));
+            if (2 * el <= r - 1) {
+                el = r - el;
+                const int ld = T.lg[discr];
+                for (int i = 0; i <= nroots; i++) b[i] = lambda[i] ? T.ex[gf_mod255(T.lg[lambda[i]] - ld + 255)] : uint8_t(0);
+            } else {
+                for (int i = nroots; i > 0; i--) b[i] = b[i - 1];
+                b[0] = 0;
+            }
+            for (int i = 0; i <= nroots; i++) lambda[i] = t[i];
+        }
+    }
+    int deg_lambda = 0;
+    for (int i = 0; i <= nroots; i++) if (lambda[i]) deg_lambda = i;
+    int count = 0;
+    for (int i = 1; i <= 255; i++) {
+        uint8_t q = 1;
+        for (int j = deg_lambda; j > 0; j--) if (lambda[j]) q ^= T.ex[gf_mod255(T.lg[lambda[j]] + (i * j) % 255)];
+        if (q != 0) continue;
+        root[count] = uint8_t(i);
+        loc[count] = uint8_t(i - 1);
+        if (++count == deg_lambda) break;
+    }
+    if (deg_lambda != count) return -1;
+    const int deg_omega = deg_lambda - 1;
+    for (int i = 0; i <= deg_omega; i++) {
+        uint8_t tmp = 0;
+        for (int j = i; j >= 0; j--) tmp ^= gf_mul_dev(T, S[i - j], lambda[j]);
+        omega[i] = tmp;
+    }
+    for (int j = count - 1; j >= 0; j--) {
+        uint8_t num1 = 0, den = 0;
+        for (int i = deg_omega; i >= 0; i--) if (omega[i]) num1 ^= T.ex[gf_mod255(T.lg[omega[i]] + (i * root[j]) % 255)];
+        const uint8_t num2 = T.ex[gf_mod255(255 - root[j])];
+        const int top = min(deg_lambda, nroots - 1) & ~1;
+        for (int i = top; i >= 0; i -= 2) if (lambda[i + 1]) den ^= T.ex[gf_mod255(T.lg[lambda[i + 1]] + (i * root[j]) % 255)];
+        apply[j] = (num1 != 0 && loc[j] >= pad) ? 1 : 0;
+        // index arithmetic kept as in the reference (log(0) = 255) so that even den == 0 gives the same byte
+        xorval[j] = T.ex[gf_mod255(int(T.lg[num1]) + int(T.lg[num2]) + 255 - int(T.lg[den]))];
+    }
+    return count;
+}
+
+struct DpShared {
+    uint8_t gf_ex[512];
+    uint8_t gf_lg[256];
+    uint16_t crc_ccitt[256];
+    uint16_t crc_fire[256];
+};
+
+__device__ __forceinline__ void dp_load_shared(DpShared& sh) {
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) sh.gf_ex[i] = c_gf_exp[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        sh.gf_lg[i] = c_gf_log[i];
+        sh.crc_ccitt[i] = c_crc_ccitt[i];
+        sh.crc_fire[i] = c_crc_fire[i];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ uint16_t crc16_tab(const uint16_t* tab, const uint8_t* p, int n, uint16_t init, uint16_t xorout) {
+    uint32_t crc = init;
+    for (int i = 0; i < n; i++) crc = ((crc << 8) ^ tab[((crc >> 8) ^ p[i]) & 0xFFu]) & 0xFFFFu;
+    return uint16_t(crc ^ xorout);
+}
+
+__device__ __forceinline__ void dp_emit(DabPlusEvent* ev, int32_t* n_ev, int type, int a, int b, int c, int d, int off, int len) {
+    const int k = *n_ev;
+    if (k < DP_MAX_EVENTS) {
+        ev[k].type = type; ev[k].a = a; ev[k].b = b; ev[k].c = c; ev[k].d = d;
+        ev[k].payload_off = off; ev[k].payload_len = len; ev[k].pad = 0;
+    }
+    *n_ev = k + 1;
+}
+
+// read_au_start (aac_frame_processor.cpp:30-72): n 12-bit values MSB first; returns bytes consumed
+__device__ int dp_read_au_start(const uint8_t* buf, uint16_t* data, int n) {
+    int bitpos = 0;
+    for (int i = 0; i < n; i++) {
+        unsigned v = 0;
+        for (int k = 0; k < 12; k++, bitpos++) v = (v << 1) | ((buf[bitpos >> 3] >> (7 - (bitpos & 7))) & 1u);
+        data[i] = uint16_t(v);
+    }
+    return (bitpos + 7) >> 3;
+}
+
+// ProcessSuperFrame for one sub-channel, executed by a full warp.  Returns nothing; state/event side effects.
+__device__ void dp_superframe(const DpShared& sh, uint8_t* sf, uint8_t* sf_out, const int sf_base, const int nb, DabPlusSubState& st,
+                              DabPlusEvent* ev, int32_t* n_ev, unsigned long long* counters, const uint32_t lane) {
+    const GfTables T{sh.gf_ex, sh.gf_lg};
+    const int total = nb * 5;
+    const int N = total / 120;
+    // ReedSolomonDecode (aac_frame_processor.cpp:322-362)
+    for (int base = 0; base < N; base += 32) {
+        const int i = base + int(lane);
+        int cnt = 0;
+        uint8_t loc[10], xv[10], ap[10];
+        if (i < N) {
+            uint8_t S[10];
+            if (rs_syndromes(T, sf + i, N, 120, 10, S)) cnt = rs_solve(T, S, 10, 135, loc, xv, ap);
+        }
+        const uint32_t fail_mask = __ballot_sync(FULL_MASK, cnt < 0);
+        const int first_fail = fail_mask ? (__ffs(int(fail_mask)) - 1) : 32;
+        if (i < N && int(lane) < first_fail) {
+            for (int j = 0; j < cnt; j++) {
+                const int k = int(loc[j]) - 135;
+                if (k >= 0 && ap[j]) sf[i + k * N] ^= xv[j];
+            }
+        }
+        __syncwarp();
+        if (fail_mask) {
+            if (lane == 0) {
+                dp_emit(ev, n_ev, DABGPU_EV_RS_ERROR, base + first_fail, N, 0, 0, 0, 0);
+                st.desync++;
+                atomicAdd(&counters[CNT_SF_RS_FAIL], 1ull);
+            }
+            return;
+        }
+    }
+    __syncwarp();
+    // fire code on the corrected superframe (aac_frame_processor.cpp:179-191, 210-213)
+    int ok = 0;
+    if (lane == 0) {
+        const uint16_t rx = uint16_t((uint16_t(sf[0]) << 8) | sf[1]);
+        const uint16_t pred = crc16_tab(sh.crc_fire, sf + 2, 9, 0, 0);
+        ok = (rx == pred);
+        if (!ok) {
+            dp_emit(ev, n_ev, DABGPU_EV_FIRECODE_ERROR, st.curr_frame, rx, pred, 0, 0, 0);
+            st.desync++;
+            atomicAdd(&counters[CNT_SF_FIRE_FAIL], 1ull);
+        }
+    }
+    ok = __shfl_sync(FULL_MASK, ok, 0);
+    if (!ok) return;
+    // the accumulator is reused by the following CIFs of this frame: keep the validated superframe for the host
+    for (int i = int(lane); i < total; i += 32) sf_out[i] = sf[i];
+    // header (aac_frame_processor.cpp:215-279)
+    const uint8_t dsc = sf[2];
+    const int dac_rate = (dsc >> 6) & 1, sbr = (dsc >> 5) & 1, ch = (dsc >> 4) & 1, ps = (dsc >> 3) & 1, mpeg = dsc & 7;
+    int num_aus = 0;
+    if (!dac_rate && sbr) num_aus = 2;
+    if (dac_rate && sbr) num_aus = 3;
+    if (!dac_rate && !sbr) num_aus = 4;
+    if (dac_rate && !sbr) num_aus = 6;
+    uint16_t au_start[7] = {0, 0, 0, 0, 0, 0, 0};
+    const int nb_tbl = dp_read_au_start(sf + 3, &au_start[1], num_aus - 1);
+    au_start[num_aus] = uint16_t(110 * N);
+    au_start[0] = uint16_t(3 + nb_tbl);
+    // per-AU CRC in parallel (lane i < num_aus), events emitted in order by lane 0
+    int au_state = 0;   // 0 = stop (bounds), 1 = crc error, 2 = ok
+    uint32_t crc_pair = 0;
+    if (int(lane) < num_aus) {
+        const int nb_au = int(au_start[lane + 1]) - int(au_start[lane]);
+        const int nb_data = nb_au - 2;
+        if (!(nb_data < 0 || int(au_start[lane + 1]) >= total)) {
+            const uint8_t* au = sf + au_start[lane];
+            const uint16_t rx = uint16_t((uint16_t(au[nb_data]) << 8) | au[nb_data + 1]);
+            const uint16_t pred = crc16_tab(sh.crc_ccitt, au, nb_data, 0xFFFF, 0xFFFF);
+            au_state = (rx == pred) ? 2 : 1;
+            crc_pair = (uint32_t(rx) << 16) | pred;
+        }
+    }
+    for (int i = 0; i < 6; i++) {
+        const int s_i = __shfl_sync(FULL_MASK, au_state, i);
+        const uint32_t c_i = __shfl_sync(FULL_MASK, crc_pair, i);
+        if (lane == 0 && i < num_aus) {
+            if (i == 0) {
+                st.desync = 0; st.synced = 1;
+                const int surround = (mpeg == 0) ? 0 : (mpeg == 1) ? 1 : (mpeg == 2) ? 2 : (mpeg == 7) ? 3 : 4;
+                dp_emit(ev, n_ev, DABGPU_EV_SUPERFRAME_HEADER, dac_rate ? 48000 : 32000, (ps ? 1 : 0) | (sbr ? 2 : 0) | (ch ? 4 : 0), surround, 0, 0, 0);
+                atomicAdd(&counters[CNT_SF_OK], 1ull);
+            }
+            if (s_i == 1) {
+                dp_emit(ev, n_ev, DABGPU_EV_AU_CRC_ERROR, i, num_aus, int(c_i >> 16), int(c_i & 0xFFFFu), 0, 0);
+                atomicAdd(&counters[CNT_AU_CRC_FAIL], 1ull);
+            } else if (s_i == 2) {
+                dp_emit(ev, n_ev, DABGPU_EV_ACCESS_UNIT, i, num_aus, 0, 0, sf_base + int(au_start[i]), int(au_start[i + 1]) - int(au_start[i]) - 2);
+                atomicAdd(&counters[CNT_AU_OK], 1ull);
+            }
+        }
+        if (i < num_aus && s_i == 0) break;   // "access unit out of bounds" => return (aac_frame_processor.cpp:289-296)
+    }
+}
+
+#define DP_WARPS 4
+__global__ void __launch_bounds__(DP_WARPS * 32)
+k_dabplus(const ChanDev C, const DabPlusDev D, const int first_stream, const int n_streams) {
+    __shared__ DpShared sh;
+    dp_load_shared(sh);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t wid = blockIdx.x * DP_WARPS + (threadIdx.x >> 5);
+    const uint32_t si = wid / C.max_subs, sub = wid - si * C.max_subs;
+    if (si >= uint32_t(n_streams)) return;
+    const uint32_t s = uint32_t(first_stream) + si;
+    const size_t idx = size_t(s) * C.max_subs + sub;
+    if (lane == 0) D.n_events[idx] = 0;
+    if (!C.status[2 * s] || sub >= C.n_subs[s]) return;
+    const SubCfgDev cfg = C.subcfg[idx];
+    if (!cfg.is_dabplus) return;
+    const uint32_t nb_cifs = C.geom.nb_cifs;
+    DabPlusSubState st = D.st[idx];
+    DabPlusEvent* ev = D.events + idx * DP_MAX_EVENTS;
+    int32_t n_ev_local = 0;
+    uint8_t* sf = D.sf + size_t(s) * (5u * CIF_OUT_STRIDE) + 5u * cfg.out_offset;
+    const int n = int(cfg.n_out_bytes);
+    for (uint32_t c = 0; c < nb_cifs; c++) {
+        if (!C.msc_valid[(size_t(s) * nb_cifs + c) * C.max_subs + sub]) continue;
+        const uint8_t* buf = C.msc_out + (size_t(s) * nb_cifs + c) * CIF_OUT_STRIDE + cfg.out_offset;
+        // AAC_Frame_Processor::Process (aac_frame_processor.cpp:126-177); all lanes keep identical copies of st
+        if (n < 11) continue;
+        if (st.prev_nb != n) { st.prev_nb = n; st.curr_frame = 0; st.collect = 0; }
+        if (st.desync >= 10) { st.desync = 0; st.synced = 0; }
+        if (st.synced) st.collect = 1;
+        if (!st.collect) {
+            int ok = 0;
+            if (lane == 0) {
+                const uint16_t rx = uint16_t((uint16_t(buf[0]) << 8) | buf[1]);
+                const uint16_t pred = crc16_tab(sh.crc_fire, buf + 2, 9, 0, 0);
+                ok = (rx == pred);
+                if (!ok) dp_emit(ev, &n_ev_local, DABGPU_EV_FIRECODE_ERROR, st.curr_frame, rx, pred, 0, 0, 0);
+            }
+            ok = __shfl_sync(FULL_MASK, ok, 0);
+            if (!ok) continue;
+            st.collect = 1;
+        }
+        for (int i = int(lane); i < n; i += 32) sf[size_t(st.curr_frame) * n + i] = buf[i];
+        __syncwarp();
+        st.curr_frame++;
+        if (st.curr_frame == 5) {
+            // lane 0 owns the mutable copy during the superframe step, then broadcasts
+            dp_superframe(sh, sf, D.sf_out + size_t(s) * (5u * CIF_OUT_STRIDE) + 5u * cfg.out_offset, int(5u * cfg.out_offset), n, st, ev,
+                          &n_ev_local, C.counters, lane);
+            st.desync = __shfl_sync(FULL_MASK, st.desync, 0);
+            st.synced = __shfl_sync(FULL_MASK, st.synced, 0);
+            st.collect = 0;
+            st.curr_frame = 0;
+        }
+    }
+    if (lane == 0) { D.st[idx] = st; D.n_events[idx] = n_ev_local; }
+}
+
+// Reed_Solomon_Decoder::Decode batched: one thread per codeword, corrected in place.
+__global__ void k_rs_batch(uint8_t* __restrict__ cw, const int n_cw, const int n, const int nroots, const int pad, int* __restrict__ counts,
+                           int* __restrict__ positions) {
+    __shared__ DpShared sh;
+    dp_load_shared(sh);
+    const GfTables T{sh.gf_ex, sh.gf_lg};
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cw) return;
+    uint8_t* data = cw + size_t(i) * n;
+    uint8_t S[RS_MAX_ROOTS], loc[RS_MAX_ROOTS], xv[RS_MAX_ROOTS], ap[RS_MAX_ROOTS];
+    int cnt = 0;
+    if (rs_syndromes(T, data, 1, n, nroots, S)) cnt = rs_solve(T, S, nroots, pad, loc, xv, ap);
+    for (int j = 0; j < cnt; j++) {
+        if (ap[j]) data[int(loc[j]) - pad] ^= xv[j];
+        if (positions) positions[size_t(i) * nroots + j] = loc[j];
+    }
+    counts[i] = cnt;
+}
+
+static int dabplus_init(DabPlusState& S, int max_streams, int max_subs, int nb_cifs) {
+    S.max_streams = max_streams; S.max_subs = max_subs; S.nb_cifs = nb_cifs;
+    int rc;
+    const size_t n = size_t(max_streams) * max_subs;
+    if ((rc = S.d_st.alloc(n * sizeof(DabPlusSubState)))) return rc;
+    if ((rc = S.d_sf.alloc(size_t(max_streams) * 5u * CIF_OUT_STRIDE))) return rc;
+    if ((rc = S.d_sf_out.alloc(size_t(max_streams) * 5u * CIF_OUT_STRIDE))) return rc;
+    if ((rc = S.d_events.alloc(n * DP_MAX_EVENTS * sizeof(DabPlusEvent)))) return rc;
+    if ((rc = S.d_nevents.alloc(n * 4))) return rc;
+    cudaMemset(S.d_st.p, 0, S.d_st.bytes);
+    cudaMemset(S.d_sf.p, 0, S.d_sf.bytes);
+    cudaMemset(S.d_sf_out.p, 0, S.d_sf_out.bytes);
+    cudaMemset(S.d_events.p, 0, S.d_events.bytes);
+    cudaMemset(S.d_nevents.p, 0, S.d_nevents.bytes);
+    S.dev.st = S.d_st.as<DabPlusSubState>();
+    S.dev.sf = S.d_sf.as<uint8_t>();
+    S.dev.sf_out = S.d_sf_out.as<uint8_t>();
+    S.dev.events = S.d_events.as<DabPlusEvent>();
+    S.dev.n_events = S.d_nevents.as<int32_t>();
+    return DABGPU_OK;
+}
+
+static void dabplus_destroy(DabPlusState& S) {
+    DevBuf* bufs[] = {&S.d_st, &S.d_sf, &S.d_sf_out, &S.d_events, &S.d_nevents, &S.d_rs_cw, &S.d_rs_cnt, &S.d_rs_pos};
+    for (DevBuf* b : bufs) b->release();
+}
+
+static int dabplus_reset_stream(DabPlusState& S, int stream) {
+    CUDA_TRY(cudaMemset(S.dev.st + size_t(stream) * S.max_subs, 0, size_t(S.max_subs) * sizeof(DabPlusSubState)));
+    CUDA_TRY(cudaMemset(S.dev.n_events + size_t(stream) * S.max_subs, 0, size_t(S.max_subs) * 4));
+    return DABGPU_OK;
+}
+
+static int dabplus_run(DabPlusState& S, const ChanDev& C, int first, int n, cudaStream_t stream, uint64_t* launches) {
+    const uint32_t warps = uint32_t(n) * uint32_t(S.max_subs);
+    k_dabplus<<<(warps + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, 0, stream>>>(C, S.dev, first, n);
+    (*launches)++;
+    CUDA_TRY(cudaGetLastError());
+    return DABGPU_OK;
+}
+
+// Host side: rebuild the flat observer log (same layout as oracle/ref_harness.cpp) from the device records.
+static int dabplus_get_events(DabPlusState& S, int stream, int sub, uint8_t* log_host, size_t log_cap, size_t* log_bytes) {
+    const size_t idx = size_t(stream) * S.max_subs + sub;
+    int32_t n_ev = 0;
+    CUDA_TRY(cudaMemcpy(&n_ev, S.dev.n_events + idx, 4, cudaMemcpyDeviceToHost));
+    if (n_ev > DP_MAX_EVENTS) return set_error(DABGPU_ERR_OVERFLOW, "event queue overflow (%d events)", n_ev);
+    DabPlusEvent ev[DP_MAX_EVENTS];
+    if (n_ev > 0) CUDA_TRY(cudaMemcpy(ev, S.dev.events + idx * DP_MAX_EVENTS, size_t(n_ev) * sizeof(DabPlusEvent), cudaMemcpyDeviceToHost));
+    size_t off = 0;
+    std::vector<uint8_t> sfbuf;
+    for (int i = 0; i < n_ev; i++) {
+        const size_t padded = (size_t(ev[i].payload_len) + 3u) & ~size_t(3);
+        if (off + 24 + padded > log_cap) return set_error(DABGPU_ERR_OVERFLOW, "event log buffer too small");
+        const int32_t hdr[6] = {ev[i].type, ev[i].a, ev[i].b, ev[i].c, ev[i].d, ev[i].payload_len};
+        memcpy(log_host + off, hdr, 24);
+        off += 24;
+        if (ev[i].payload_len > 0) {
+            // payloads (access units) live in the corrected superframe buffer of the sub-channel
+            if (sfbuf.empty()) {
+                sfbuf.resize(5u * CIF_OUT_STRIDE);
+                CUDA_TRY(cudaMemcpy(sfbuf.data(), S.dev.sf_out + size_t(stream) * (5u * CIF_OUT_STRIDE), sfbuf.size(), cudaMemcpyDeviceToHost));
+            }
+            memset(log_host + off, 0, padded);
+            // payload_off is an offset inside the stream's superframe arena
+            memcpy(log_host + off, sfbuf.data() + size_t(ev[i].payload_off), size_t(ev[i].payload_len));
+            off += padded;
+        }
+    }
+    if (log_bytes) *log_bytes = off;
+    return DABGPU_OK;
+}
+
+static int dabplus_rs_decode_batch(DabPlusState& S, uint8_t* cw_host, int n_cw, int nroots, int pad, int* counts_host, int* pos_host,
+                                   cudaStream_t stream, uint64_t* launches) {
+    if (n_cw <= 0) return DABGPU_OK;
+    if (nroots < 1 || nroots > RS_MAX_ROOTS) return set_error(DABGPU_ERR_INVALID, "nroots %d out of range", nroots);
+    if (pad < 0 || pad >= 255 - nroots) return set_error(DABGPU_ERR_INVALID, "pad %d out of range", pad);
+    const int n = 255 - pad;
+    int rc;
+    if ((rc = S.d_rs_cw.alloc(size_t(n_cw) * n))) return rc;
+    if ((rc = S.d_rs_cnt.alloc(size_t(n_cw) * 4))) return rc;
+    if ((rc = S.d_rs_pos.alloc(size_t(n_cw) * nroots * 4))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(S.d_rs_cw.p, cw_host, size_t(n_cw) * n, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemsetAsync(S.d_rs_pos.p, 0, size_t(n_cw) * nroots * 4, stream));
+    k_rs_batch<<<(n_cw + 63) / 64, 64, 0, stream>>>(S.d_rs_cw.as<uint8_t>(), n_cw, n, nroots, pad, S.d_rs_cnt.as<int>(), S.d_rs_pos.as<int>());
+    (*launches)++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(cw_host, S.d_rs_cw.p, size_t(n_cw) * n, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(counts_host, S.d_rs_cnt.p, size_t(n_cw) * 4, cudaMemcpyDeviceToHost, stream));
+    if (pos_host) CUDA_TRY(cudaMemcpyAsync(pos_host, S.d_rs_pos.p, size_t(n_cw) * nroots * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return DABGPU_OK;
+}

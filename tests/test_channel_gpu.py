@@ -1,0 +1,231 @@
+"""GPU parity of the integer half of the chain (through the C ABI) against both oracles.
+
+Bar: bit-exact decoded bytes, path errors, CRC flags, RS corrections and superframe events.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk_trellis_cases(tx, rng, n):
+    seg_choices = [tx.FIC_SEGMENTS, tx.eep_segments(48, 2, False), tx.eep_segments(8, 1, False), tx.uep_segments(4),
+                   tx.eep_segments(54, 2, True), tx.eep_segments(96, 0, False), tx.eep_segments(40, 3, False), tx.uep_segments(0)]
+    softs, segs = [], []
+    for trial in range(n):
+        sg = seg_choices[trial % len(seg_choices)]
+        n_in = int(tx.puncture_mask(sg).sum())
+        info = rng.integers(0, 256, size=(sum(b for _, b in sg) // 4 - 6) // 8, dtype=np.uint8)
+        enc = tx.channel_encode(info, sg)
+        kind = (trial // len(seg_choices)) % 5
+        if kind == 0:
+            soft = tx.hard_to_soft(enc)                                           # noiseless
+        elif kind == 1:
+            soft = tx.hard_to_soft(enc, rng, snr_db=float(rng.uniform(-6, 6)))    # noisy
+        elif kind == 2:
+            soft = rng.integers(-128, 128, size=n_in).astype(np.int8)             # garbage incl. -128
+        elif kind == 3:
+            soft = (rng.integers(-1, 2, size=n_in) * 127).astype(np.int8)         # tie heavy
+        else:
+            soft = np.where(rng.random(n_in) < 0.5, -128, 127).astype(np.int8)    # saturating metrics
+        softs.append(soft)
+        segs.append(sg)
+    return softs, segs
+
+
+def test_viterbi_matches_oracles(gpu_ctx, tx, pyref):
+    rng = np.random.default_rng(11)
+    softs, segs = _mk_trellis_cases(tx, rng, 160)
+    g = gpu_ctx.DabGpu(mode=1, max_streams=1)
+    outs, perr = g.viterbi_decode(softs, segs)
+    port = pyref.PortViterbi()
+    ref = pyref.RefViterbi() if pyref.ref_available() else None
+    for i, (soft, sg) in enumerate(zip(softs, segs)):
+        exp, _, exp_err = port.decode(soft, sg)
+        assert np.array_equal(outs[i], exp), f"trellis {i}: bytes differ from the C restatement"
+        assert int(perr[i]) == exp_err, f"trellis {i}: path error {int(perr[i])} != {exp_err}"
+        if ref is not None:
+            r, _, r_err = ref.decode(soft, sg)
+            assert np.array_equal(outs[i], r), f"trellis {i}: bytes differ from the reference build"
+            assert int(perr[i]) == r_err
+    g.close()
+
+
+def test_viterbi_long_trellis_and_renormalisation(gpu_ctx, tx, pyref):
+    # 864 CU at EEP 4-A: 27654 steps; noisy input forces several renormalisations
+    rng = np.random.default_rng(12)
+    sg = tx.eep_segments(864, 3, False)
+    n_in = int(tx.puncture_mask(sg).sum())
+    info = rng.integers(0, 256, size=(sum(b for _, b in sg) // 4 - 6) // 8, dtype=np.uint8)
+    enc = tx.channel_encode(info, sg)
+    softs = [tx.hard_to_soft(enc, rng, snr_db=-3.0), rng.integers(-128, 128, size=n_in).astype(np.int8)]
+    g = gpu_ctx.DabGpu(mode=1, max_streams=1)
+    outs, perr = g.viterbi_decode(softs, [sg, sg], descramble=True)
+    port = pyref.PortViterbi()
+    prbs = pyref.port_scrambler_bytes(outs[0].size)
+    for i in range(2):
+        exp, _, exp_err = port.decode(softs[i], sg)
+        assert np.array_equal(outs[i], exp ^ prbs)
+        assert int(perr[i]) == exp_err
+    g.close()
+
+
+def test_viterbi_bad_arguments(gpu_ctx, tx):
+    g = gpu_ctx.DabGpu(mode=1, max_streams=1)
+    soft = np.zeros(100, dtype=np.int8)
+    with pytest.raises(gpu_ctx.DabGpuError) as e:
+        g.viterbi_decode([soft], [tx.FIC_SEGMENTS])      # not enough punctured symbols
+    assert e.value.code == gpu_ctx.ERR_INVALID
+    with pytest.raises(gpu_ctx.DabGpuError):
+        g.viterbi_decode([np.zeros(2304, np.int8)], [[(25, 128), (0, 24)]])   # invalid puncture code
+    g.close()
+
+
+def _subs(tx):
+    return [tx.Subchannel(0, 0, 48, eep_level=2), tx.Subchannel(1, 48, 8, eep_level=1, dabplus=False),
+            tx.Subchannel(2, 56, 54, eep_level=2, eep_type_b=True, dabplus=False),
+            tx.Subchannel(3, 110, 35, is_uep=True, uep_index=4, dabplus=False),
+            tx.Subchannel(4, 145, 16, is_uep=True, uep_index=0, dabplus=False),
+            tx.Subchannel(5, 200, 96, eep_level=0), tx.Subchannel(6, 300, 40, eep_level=3)]
+
+
+@pytest.mark.parametrize("snr_db", [None, 4.0])
+def test_frame_decode_fic_msc_dabplus(gpu_ctx, tx, pyref, snr_db):
+    """Soft-bit frames in -> FIBs, sub-channel bytes, superframe events out; two streams with different seeds."""
+    rng = np.random.default_rng(21)
+    subs = _subs(tx)
+    n_streams, n_frames = 2, 12
+    g = gpu_ctx.DabGpu(mode=1, max_streams=n_streams)
+    enss = [tx.EnsembleTx(1, subs, seed=100 + s) for s in range(n_streams)]
+    use_ref = pyref.ref_available()
+    mk_msc = (lambda sc: pyref.RefMsc(sc.start_address, sc.length, sc.is_uep, sc.uep_index, sc.eep_level, sc.eep_type_b)) if use_ref else \
+             (lambda sc: pyref.PortMsc(sc.start_address, sc.length, sc.is_uep, sc.uep_index, sc.eep_level, sc.eep_type_b))
+    o_msc = [[mk_msc(sc) for sc in subs] for _ in range(n_streams)]
+    o_aac = [[(pyref.RefAac() if use_ref else pyref.PortAac()) if sc.dabplus else None for sc in subs] for _ in range(n_streams)]
+    o_fic = pyref.RefFic() if use_ref else pyref.PortFic()
+    for s in range(n_streams):
+        g.msc_configure(s, subs)
+    n_checked_bytes = 0
+    n_events = 0
+    for f in range(n_frames):
+        frames = np.stack([tx.hard_to_soft(e.next_frame_bits(), rng, snr_db=snr_db) for e in enss])
+        g.softbits_push(frames)
+        g.chan_decode()
+        for s in range(n_streams):
+            decoded, idx = g.chan_status(s)
+            assert decoded == 1 and idx == f
+            fibs, ok = g.get_fic(s)
+            exp_fibs = []
+            for c in range(4):
+                exp_fibs += o_fic.decode_group(frames[s, c * 2304:(c + 1) * 2304], c)
+            got_fibs = [fibs[i, :30].tobytes() for i in range(12) if ok[i]]
+            assert got_fibs == exp_fibs
+            for k, sc in enumerate(subs):
+                out, valid = g.get_msc(s, k)
+                log = b""
+                for c in range(4):
+                    cif = frames[s, 9216 + c * 55296: 9216 + (c + 1) * 55296]
+                    exp = o_msc[s][k].decode_cif(cif)
+                    assert bool(valid[c]) == (exp.size > 0), (f, s, k, c)
+                    if exp.size:
+                        assert np.array_equal(out[c], exp), (f, s, k, c)
+                        n_checked_bytes += exp.size
+                        if sc.dabplus:
+                            for ev in o_aac[s][k].process(exp):
+                                log += np.array(ev[:5] + (len(ev[5]),), dtype=np.int32).tobytes() + ev[5] + b"\0" * ((-len(ev[5])) % 4)
+                if sc.dabplus:
+                    got = g.get_dabplus_events(s, k)
+                    assert got == log, (f, s, k, pyref.parse_event_log(got)[:3], pyref.parse_event_log(log)[:3])
+                    n_events += len(pyref.parse_event_log(log))
+    assert n_checked_bytes > 0 and n_events > 0
+    c = g.counters()
+    assert c["frames_channel_decoded"] == n_streams * n_frames
+    g.close()
+
+
+def test_dabplus_with_byte_errors(gpu_ctx, tx, pyref):
+    """Superframes with injected byte errors: <=5 per codeword corrected, >5 uncorrectable, fire-code resync."""
+    rng = np.random.default_rng(5)
+    sc = tx.Subchannel(0, 0, 48, eep_level=2)
+    g = gpu_ctx.DabGpu(mode=1, max_streams=1)
+    g.msc_configure(0, [sc])
+    ens = tx.EnsembleTx(1, [sc], seed=9)
+    # corrupt the payload before channel coding by patching the transmitter's superframe builder
+    orig = tx.build_superframe
+    counter = {"n": 0}
+
+    def corrupt(*a, **k):
+        sf = orig(*a, **k)
+        n = counter["n"]
+        counter["n"] += 1
+        ncw = sf.size // 120
+        if n % 4 == 1:      # correctable: up to 5 errors in some codewords
+            for cw in range(0, ncw, 2):
+                for j in rng.choice(120, size=int(rng.integers(1, 6)), replace=False):
+                    sf[cw + j * ncw] ^= rng.integers(1, 256)
+        elif n % 4 == 2:    # uncorrectable codeword 3
+            for j in rng.choice(120, size=9, replace=False):
+                sf[3 + j * ncw] ^= rng.integers(1, 256)
+        elif n % 4 == 3:    # broken AU CRC without touching RS: flip payload byte and re-encode parity is not done => RS fixes it
+            sf[40] ^= 0x55
+        return sf
+
+    tx.build_superframe = corrupt
+    try:
+        use_ref = pyref.ref_available()
+        o_msc = pyref.RefMsc(0, 48) if use_ref else pyref.PortMsc(0, 48)
+        o_aac = pyref.RefAac() if use_ref else pyref.PortAac()
+        kinds = set()
+        for f in range(24):
+            frame = tx.hard_to_soft(ens.next_frame_bits())[None, :]
+            g.softbits_push(frame)
+            g.chan_decode()
+            log = b""
+            for c in range(4):
+                exp = o_msc.decode_cif(frame[0, 9216 + c * 55296: 9216 + (c + 1) * 55296])
+                if exp.size:
+                    for ev in o_aac.process(exp):
+                        kinds.add(ev[0])
+                        log += np.array(ev[:5] + (len(ev[5]),), dtype=np.int32).tobytes() + ev[5] + b"\0" * ((-len(ev[5])) % 4)
+            assert g.get_dabplus_events(0, 0) == log, f
+        assert {pyref.EV_RS_ERROR, pyref.EV_HEADER, pyref.EV_AU} <= kinds
+    finally:
+        tx.build_superframe = orig
+    g.close()
+
+
+def test_rs_batch_matches_oracle(gpu_ctx, tx, pyref):
+    rng = np.random.default_rng(3)
+    n = 600
+    cws = np.zeros((n, 120), dtype=np.uint8)
+    for t in range(n):
+        data = rng.integers(0, 256, size=110).tolist()
+        cw = np.array(data + tx.rs_encode(data, 10), dtype=np.uint8)
+        for p in rng.choice(120, size=t % 9, replace=False):
+            cw[p] ^= rng.integers(1, 256)
+        if t % 50 == 49:
+            cw = rng.integers(0, 256, size=120).astype(np.uint8)
+        cws[t] = cw
+    g = gpu_ctx.DabGpu(mode=1, max_streams=1)
+    counts, fixed, pos = g.rs_decode(cws)
+    o = pyref.RefRS() if pyref.ref_available() else pyref.PortRS()
+    for t in range(n):
+        c, d, p = o.decode(cws[t])
+        assert counts[t] == c, t
+        assert np.array_equal(fixed[t], d), t
+        if c > 0:
+            assert np.array_equal(pos[t, :c], p), t
+    # packet-mode code RS(204,188): 16 roots, pad 51 (msc_reed_solomon_data_packet_processor.cpp:21-26)
+    cws2 = np.zeros((64, 204), dtype=np.uint8)
+    for t in range(64):
+        data = rng.integers(0, 256, size=188).tolist()
+        cw = np.array(data + tx.rs_encode(data, 16), dtype=np.uint8)
+        for p in rng.choice(204, size=t % 11, replace=False):
+            cw[p] ^= rng.integers(1, 256)
+        cws2[t] = cw
+    counts2, fixed2, _ = g.rs_decode(cws2, nroots=16, pad=51)
+    o2 = pyref.RefRS(16, 51) if pyref.ref_available() else pyref.PortRS(16, 51)
+    for t in range(64):
+        c, d, _ = o2.decode(cws2[t])
+        assert counts2[t] == c and np.array_equal(fixed2[t], d), t
+    g.close()
