@@ -1,0 +1,145 @@
+"""GPU parity of the OFDM half (through the C ABI) against the reference OFDM_Demod (serialised driver)
+and the C restatement.  Bar (BASELINE.json north_star): same frames out, same sync decisions,
+max |delta| of one soft-bit quantisation step, identical post-Viterbi bytes.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SOFT_TOL = 1   # one quantisation step of the int8 soft decision
+
+
+def _recording(tx, mode, n_frames, snr_db, cfo, lead, seed, subs=None):
+    ens = tx.EnsembleTx(mode, subs if subs is not None else tx.default_ensemble(), seed=seed)
+    frames = [ens.next_frame_bits() for _ in range(n_frames)]
+    iq = tx.ofdm_modulate(frames, mode)
+    x = tx.impair(iq, snr_db, cfo, lead, seed=seed + 1000, tail_samples=3000)
+    return tx.to_u8(x, 30.0), frames, ens
+
+
+def _oracle(pyref, mode):
+    return pyref.RefOfdm(mode, 1) if pyref.ref_available() else pyref.PortOfdm(mode)
+
+
+def _feed(o, u8, block):
+    for off in range(0, u8.size // 2, block):
+        o.process_u8(u8[2 * off:2 * (off + block)])
+    return o.pop_frames()
+
+
+@pytest.mark.parametrize("mode,block,cfo,snr", [(1, 65536, 1.8e-3, 20.0), (1, 65536, -9.87e-3, 12.0), (2, 65536, 3.3e-3, 15.0),
+                                                (4, 65536, -2.2e-3, 15.0), (1, 8192, 0.0, 25.0), (3, 4096, 1.0e-3, 20.0)])
+def test_ofdm_soft_bits_match_reference(gpu_ctx, tx, pyref, mode, block, cfo, snr):
+    n_frames = 5 if mode == 1 else 10
+    u8, txframes, _ = _recording(tx, mode, n_frames, snr, cfo, 1234, seed=mode * 10 + 1)
+    exp = _feed(_oracle(pyref, mode), u8, block)
+    g = gpu_ctx.DabGpu(mode=mode, max_streams=1)
+    got = []
+    for off in range(0, u8.size // 2, block):
+        g.ofdm_process(u8[None, 2 * off:2 * (off + block)], block_size=block)
+        got += g.ofdm_pop_frames(0)
+    assert len(got) == len(exp), (len(got), len(exp), g.ofdm_status(0))
+    for i, (a, b) in enumerate(zip(got, exp)):
+        assert a[3] == b[3], f"frame {i}: fine time offset {a[3]} != {b[3]}"
+        d = np.abs(a[0].astype(np.int32) - b[0].astype(np.int32))
+        assert d.max() <= SOFT_TOL, f"frame {i}: max soft-bit delta {d.max()} (n>{SOFT_TOL}: {(d > SOFT_TOL).sum()})"
+        assert abs(a[1] - b[1]) < 2e-6 and abs(a[2] - b[2]) < 2e-6, (i, a[1:3], b[1:3])
+    if len(exp) > 2:
+        # the recovered bits are the transmitted ones (sanity of the whole comparison)
+        hard = (got[2][0] > 0).astype(np.uint8)
+        assert min(int(np.sum(hard != f)) for f in txframes) < 0.05 * hard.size
+    g.close()
+
+
+def test_ofdm_multi_stream_ragged_and_post_viterbi_identical(gpu_ctx, tx, pyref):
+    """4 streams with different CFO / timing / SNR in one batch; decoded FIC+MSC bytes equal the reference chain's."""
+    mode, block = 1, 65536
+    subs = [tx.Subchannel(0, 0, 48, eep_level=2), tx.Subchannel(1, 48, 54, eep_level=2, eep_type_b=True, dabplus=False),
+            tx.Subchannel(2, 110, 35, is_uep=True, uep_index=4, dabplus=False)]
+    cfg = [(20.0, 1.8e-3, 1234), (10.0, -4.1e-3, 77), (15.0, 7.7e-3, 150000), (8.0, 0.2e-3, 99999)]
+    n_frames = 7
+    recs = [_recording(tx, mode, n_frames, snr, cfo, lead, seed=50 + i, subs=subs) for i, (snr, cfo, lead) in enumerate(cfg)]
+    n = min(r[0].size for r in recs) // 2
+    n = (n // block) * block
+    g = gpu_ctx.DabGpu(mode=mode, max_streams=len(recs))
+    for s in range(len(recs)):
+        g.msc_configure(s, subs)
+    oracles = [_oracle(pyref, mode) for _ in recs]
+    use_ref = pyref.ref_available()
+    mk = pyref.RefMsc if use_ref else pyref.PortMsc
+    o_msc = [[mk(sc.start_address, sc.length, sc.is_uep, sc.uep_index, sc.eep_level, sc.eep_type_b) for sc in subs] for _ in recs]
+    o_fic = pyref.RefFic() if use_ref else pyref.PortFic()
+    total_frames = 0
+    for off in range(0, n, block):
+        batch = np.stack([r[0][2 * off:2 * (off + block)] for r in recs])
+        g.ofdm_process(batch, block_size=block)
+        for s, o in enumerate(oracles):
+            o.process_u8(recs[s][0][2 * off:2 * (off + block)])
+        # channel decode whatever the OFDM stage produced, on the device, and compare with the reference chain fed by ITS soft bits
+        g.chan_decode()
+        for s, o in enumerate(oracles):
+            exp_frames = o.pop_frames()
+            got_frames = g.ofdm_pop_frames(s)
+            assert len(got_frames) == len(exp_frames), (off, s)
+            decoded, _ = g.chan_status(s)
+            assert decoded == (1 if exp_frames else 0)
+            for (gb, _, _, gt), (eb, _, _, et) in zip(got_frames, exp_frames):
+                total_frames += 1
+                assert gt == et
+                assert np.abs(gb.astype(np.int32) - eb.astype(np.int32)).max() <= SOFT_TOL
+                fibs, ok = g.get_fic(s)
+                exp_fibs = []
+                for c in range(4):
+                    exp_fibs += o_fic.decode_group(eb[c * 2304:(c + 1) * 2304], c)
+                assert [fibs[i, :30].tobytes() for i in range(12) if ok[i]] == exp_fibs
+                for k in range(len(subs)):
+                    out, valid = g.get_msc(s, k)
+                    for c in range(4):
+                        e = o_msc[s][k].decode_cif(eb[9216 + c * 55296:9216 + (c + 1) * 55296])
+                        assert bool(valid[c]) == (e.size > 0)
+                        if e.size:
+                            assert np.array_equal(out[c], e), (off, s, k, c)
+    assert total_frames >= 4 * (n_frames - 2)
+    g.close()
+
+
+def test_ofdm_c32_input_and_device_attach(gpu_ctx, tx, pyref):
+    """complex<float> input (the OFDM_Demod::Process interface) and caller-owned device memory (torch) give the same frames."""
+    torch = pytest.importorskip("torch")
+    mode, block = 2, 65536
+    u8, _, _ = _recording(tx, mode, 8, 18.0, 2.5e-3, 500, seed=7)
+    c32 = ((u8.astype(np.float32) - np.float32(127.5)) * np.float32(1.0 / 127.5)).view(np.complex64)
+    n = (c32.size // block) * block
+    g1 = gpu_ctx.DabGpu(mode=mode, max_streams=1, iq_format=gpu_ctx.IQ_C32)
+    g2 = gpu_ctx.DabGpu(mode=mode, max_streams=1, iq_format=gpu_ctx.IQ_U8)
+    dev = torch.from_numpy(u8[:2 * n].copy()).cuda()
+    g2.ofdm_attach_device_input(dev.data_ptr(), n, n)
+    f1, f2 = [], []
+    for off in range(0, n, block):
+        g1.ofdm_process(c32[None, off:off + block], block_size=block)
+        g2.ofdm_advance(block, block_size=block)
+        f1 += g1.ofdm_pop_frames(0)
+        f2 += g2.ofdm_pop_frames(0)
+    o = _oracle(pyref, mode)
+    exp = _feed(o, u8[:2 * n], block)
+    assert len(f1) == len(f2) == len(exp) > 3
+    for a, b, e in zip(f1, f2, exp):
+        assert np.array_equal(a[0], b[0])          # identical arithmetic on both input paths
+        assert np.abs(a[0].astype(np.int32) - e[0].astype(np.int32)).max() <= SOFT_TOL
+    g1.close()
+    g2.close()
+
+
+def test_ofdm_reset_and_noise_only(gpu_ctx, tx):
+    """Noise only input never locks (desync counter runs like the reference's), Reset() returns to the null search."""
+    rng = np.random.default_rng(1)
+    g = gpu_ctx.DabGpu(mode=1, max_streams=2)
+    noise = rng.integers(100, 156, size=(2, 2 * 65536 * 4), dtype=np.uint8)
+    g.ofdm_process(noise, block_size=65536)
+    st = g.ofdm_status(0)
+    assert st["total_frames_read"] == 0 and st["frames_queued"] == 0
+    g.ofdm_reset(1)
+    st1 = g.ofdm_status(1)
+    assert st1["state"] == 0 and st1["freq_coarse_offset"] == 0.0
+    g.close()
