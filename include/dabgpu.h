@@ -79,6 +79,14 @@ DABGPU_API void* dabgpu_cuda_stream(dabgpu_ctx* ctx);              /* the stream
 /* number of kernels of this library launched on the context so far (bench.py "gpu_launches") */
 DABGPU_API uint64_t dabgpu_launch_count(const dabgpu_ctx* ctx);
 
+/* Device-side timing of the library's kernels by class (CUDA events on the launching stream), for roofline
+ * reports.  The analogue of the reference's in-process profiler (ofdm/profiler.h).  Disabled by default. */
+enum { DABGPU_PROF_OFDM_CTL = 0, DABGPU_PROF_OFDM_DEMOD = 1, DABGPU_PROF_VITERBI = 2, DABGPU_PROF_DABPLUS = 3,
+       DABGPU_PROF_CHAN_MISC = 4, DABGPU_PROF_CLASSES = 5 };
+typedef struct { double ms[DABGPU_PROF_CLASSES]; uint64_t launches[DABGPU_PROF_CLASSES]; } dabgpu_profile;
+DABGPU_API int dabgpu_profile_enable(dabgpu_ctx* ctx, int on);   /* also clears the accumulated totals */
+DABGPU_API int dabgpu_profile_read(dabgpu_ctx* ctx, dabgpu_profile* out);
+
 /* Frame geometry: OFDM_Params (ofdm/ofdm_params.h) + DAB_Parameters (dab/constants/dab_parameters.h:5-24) */
 typedef struct {
     int nb_frame_symbols, nb_symbol_period, nb_null_period, nb_cyclic_prefix, nb_fft, nb_data_carriers;

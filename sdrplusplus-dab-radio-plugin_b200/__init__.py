@@ -75,7 +75,14 @@ class Counters(C.Structure):
                                           "superframes_ok", "superframes_rs_fail", "superframes_firecode_fail", "au_ok", "au_crc_fail")]
 
 
+class Profile(C.Structure):
+    _fields_ = [("ms", C.c_double * 5), ("launches", C.c_uint64 * 5)]
+
+
+PROF_CLASSES = ("ofdm_ctl", "ofdm_demod", "viterbi", "dabplus", "chan_misc")
+
 EXPORTS = [
+    "dabgpu_profile_enable", "dabgpu_profile_read",
     "dabgpu_version", "dabgpu_last_error", "dabgpu_device_count", "dabgpu_config_default", "dabgpu_ctx_create", "dabgpu_ctx_destroy",
     "dabgpu_sync", "dabgpu_cuda_stream", "dabgpu_launch_count", "dabgpu_get_params", "dabgpu_ofdm_reset", "dabgpu_ofdm_process",
     "dabgpu_ofdm_attach_device_input", "dabgpu_ofdm_advance", "dabgpu_ofdm_get_status", "dabgpu_ofdm_pop_frames",
@@ -108,6 +115,8 @@ def load_library() -> C.CDLL:
     L.dabgpu_launch_count.argtypes = [C.c_void_p]
     L.dabgpu_launch_count.restype = C.c_uint64
     L.dabgpu_get_params.argtypes = [C.c_int, C.POINTER(Params)]
+    L.dabgpu_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.dabgpu_profile_read.argtypes = [C.c_void_p, C.POINTER(Profile)]
     L.dabgpu_ofdm_reset.argtypes = [C.c_void_p, C.c_int]
     L.dabgpu_ofdm_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int]
     L.dabgpu_ofdm_attach_device_input.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
@@ -190,6 +199,14 @@ class DabGpu:
     @property
     def launch_count(self) -> int:
         return int(self.L.dabgpu_launch_count(self.h))
+
+    def profile_enable(self, on: bool = True):
+        _check(self.L.dabgpu_profile_enable(self.h, int(on)))
+
+    def profile_read(self) -> dict:
+        p = Profile()
+        _check(self.L.dabgpu_profile_read(self.h, C.byref(p)))
+        return {name: {"ms": p.ms[i], "launches": int(p.launches[i])} for i, name in enumerate(PROF_CLASSES)}
 
     # ---- Viterbi -------------------------------------------------------------------------
     def viterbi_decode(self, soft_list: Sequence[np.ndarray], segments_list: Sequence[Sequence[Tuple[int, int]]],

@@ -105,3 +105,43 @@ struct PinnedBuf {
     }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
+
+// Optional per-kernel-class device timing (CUDA events on the launching stream), used by bench.py for the
+// roofline of the dominant kernel.  Off by default: no events are recorded on the product path.
+enum { PROF_OFDM_CTL = 0, PROF_OFDM_DEMOD = 1, PROF_VITERBI = 2, PROF_DABPLUS = 3, PROF_CHAN_MISC = 4, PROF_CLASSES = 5 };
+struct Profiler {
+    bool on = false;
+    struct Rec { int cls; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    double ms[PROF_CLASSES] = {0, 0, 0, 0, 0};
+    unsigned long long n[PROF_CLASSES] = {0, 0, 0, 0, 0};
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void begin(int cls, cudaStream_t s) {
+        if (!on) return;
+        if (recs.size() >= 8192) collect();
+        Rec r; r.cls = cls; r.a = get(); r.b = get();
+        cudaEventRecord(r.a, s);
+        recs.push_back(r);
+    }
+    void end(cudaStream_t s) {
+        if (!on) return;
+        cudaEventRecord(recs.back().b, s);
+    }
+    void collect() {
+        for (auto& r : recs) {
+            cudaEventSynchronize(r.b);
+            float t = 0.0f;
+            if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.cls] += t; n[r.cls]++; }
+            pool.push_back(r.a); pool.push_back(r.b);
+        }
+        recs.clear();
+    }
+    void reset() { collect(); for (int i = 0; i < PROF_CLASSES; i++) { ms[i] = 0; n[i] = 0; } }
+    void destroy() { collect(); for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
+};

@@ -22,6 +22,7 @@ struct dabgpu_ctx {
     int num_sms = 0;
     uint64_t launches = 0;
     int frame_slots = 0, max_subs = 0;
+    Profiler prof;
 
     // Viterbi
     DevBuf d_prbs, d_counter, d_scratch, d_jobs;
@@ -211,6 +212,7 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
     C.counters = ctx->d_counters.as<unsigned long long>();
 
     TRY_OR_FREE(dabplus_init(ctx->dabplus, S, ctx->max_subs, P.nb_cifs));
+    ctx->ofdm.prof = &ctx->prof;
     TRY_OR_FREE(ofdm_init(ctx->ofdm, ctx->cfg, P, ctx->frame_slots, ctx->d_frames.as<int8_t>(), ctx->d_frames_written.as<uint32_t>(),
                           ctx->d_frame_info.as<dabgpu_frame_info>(), ctx->d_counters.as<unsigned long long>()));
     cudaError_t e = cudaDeviceSynchronize();
@@ -223,6 +225,7 @@ void dabgpu_ctx_destroy(dabgpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ctx->prof.destroy();
     ofdm_destroy(ctx->ofdm);
     dabplus_destroy(ctx->dabplus);
     DevBuf* bufs[] = {&ctx->d_prbs, &ctx->d_counter, &ctx->d_scratch, &ctx->d_jobs, &ctx->d_vsoft, &ctx->d_vout, &ctx->d_verr,
@@ -245,14 +248,33 @@ int dabgpu_sync(dabgpu_ctx* ctx) {
 void* dabgpu_cuda_stream(dabgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t dabgpu_launch_count(const dabgpu_ctx* ctx) { return ctx ? ctx->launches + ctx->ofdm.launches : 0; }
 
+int dabgpu_profile_enable(dabgpu_ctx* ctx, int on) {
+    if (!ctx) return set_error(DABGPU_ERR_INVALID, "null context");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    ctx->prof.reset();
+    ctx->prof.on = on != 0;
+    return DABGPU_OK;
+}
+
+int dabgpu_profile_read(dabgpu_ctx* ctx, dabgpu_profile* out) {
+    if (!ctx || !out) return set_error(DABGPU_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->prof.collect();
+    for (int i = 0; i < PROF_CLASSES; i++) { out->ms[i] = ctx->prof.ms[i]; out->launches[i] = ctx->prof.n[i]; }
+    return DABGPU_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Viterbi
 // ---------------------------------------------------------------------------------------------
 static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs) {
     CUDA_TRY(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
     const int blocks = ctx->vit_blocks;
+    ctx->prof.begin(PROF_VITERBI, ctx->stream);
     k_viterbi<<<blocks, VIT_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(d_jobs, n_jobs, ctx->d_counter.as<int>(), ctx->d_scratch.as<uint2>(),
                                                                      ctx->scratch_steps, ctx->d_prbs.as<uint32_t>(), ctx->chan.geom);
+    ctx->prof.end(ctx->stream);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return DABGPU_OK;
@@ -418,11 +440,15 @@ int dabgpu_chan_decode(dabgpu_ctx* ctx, int first, int n) {
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     const uint32_t total = uint32_t(n) * ctx->chan.jobs_per_stream;
     if ((rc = ctx->d_jobs.alloc(size_t(total) * sizeof(VitJobDev)))) return rc;
+    ctx->prof.begin(PROF_CHAN_MISC, ctx->stream);
     k_chan_build_jobs<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->chan, ctx->d_jobs.as<VitJobDev>(), first, n);
+    ctx->prof.end(ctx->stream);
     ctx->launches++;
     if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), int(total)))) return rc;
-    if ((rc = dabplus_run(ctx->dabplus, ctx->chan, first, n, ctx->stream, &ctx->launches))) return rc;
+    if ((rc = dabplus_run(ctx->dabplus, ctx->chan, first, n, ctx->stream, &ctx->launches, ctx->prof))) return rc;
+    ctx->prof.begin(PROF_CHAN_MISC, ctx->stream);
     k_chan_finish<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->chan, first, n);
+    ctx->prof.end(ctx->stream);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return DABGPU_OK;

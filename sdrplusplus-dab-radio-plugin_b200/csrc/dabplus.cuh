@@ -362,9 +362,11 @@ static int dabplus_reset_stream(DabPlusState& S, int stream) {
     return DABGPU_OK;
 }
 
-static int dabplus_run(DabPlusState& S, const ChanDev& C, int first, int n, cudaStream_t stream, uint64_t* launches) {
+static int dabplus_run(DabPlusState& S, const ChanDev& C, int first, int n, cudaStream_t stream, uint64_t* launches, Profiler& pf) {
     const uint32_t warps = uint32_t(n) * uint32_t(S.max_subs);
+    pf.begin(PROF_DABPLUS, stream);
     k_dabplus<<<(warps + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, 0, stream>>>(C, S.dev, first, n);
+    pf.end(stream);
     (*launches)++;
     CUDA_TRY(cudaGetLastError());
     return DABGPU_OK;

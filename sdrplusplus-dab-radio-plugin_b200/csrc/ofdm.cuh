@@ -725,6 +725,7 @@ __global__ void k_ofdm_reset(const OfdmDev D, const int stream, const int n_stre
 // ---------------------------------------------------------------------------------------------
 struct OfdmState {
     uint64_t launches = 0;
+    Profiler* prof = nullptr;
     OfdmDev dev;
     dabgpu_params P;
     int max_streams = 0, frame_slots = 0;
@@ -925,12 +926,19 @@ template <int N>
 static int ofdm_run_t(OfdmState& O, int first, int n, int n_samples, int block_size, cudaStream_t cs) {
     const int max_frames = n_samples / O.P.nb_frame_samples + 2;
     const dim3 dgrid(O.dev.g.n_chunks, n);
+    Profiler& pf = *O.prof;
     for (int it = 0; it < max_frames; it++) {
+        pf.begin(PROF_OFDM_CTL, cs);
         k_ofdm_ctl<N><<<n, N / 8, 0, cs>>>(O.dev, first, n_samples, block_size, it == 0 ? 1 : 0);
+        pf.end(cs);
+        pf.begin(PROF_OFDM_DEMOD, cs);
         k_ofdm_demod<N><<<dgrid, N / 8, 0, cs>>>(O.dev, first);
+        pf.end(cs);
         O.launches += 2;
     }
+    pf.begin(PROF_OFDM_CTL, cs);
     k_ofdm_ctl<N><<<n, N / 8, 0, cs>>>(O.dev, first, n_samples, block_size, 0);
+    pf.end(cs);
     O.launches++;
     CUDA_TRY(cudaGetLastError());
     return DABGPU_OK;
