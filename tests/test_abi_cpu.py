@@ -1,0 +1,87 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/dabgpu.h declares; host-side logic."""
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "dabgpu.h")).read()
+    return sorted(set(re.findall(r"DABGPU_API\s+[\w\s\*]+?\b(dabgpu_\w+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(dab):
+    names = _declared_symbols()
+    assert len(names) >= 25
+    L = dab.load_library()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert set(dab.EXPORTS) == set(names), set(dab.EXPORTS) ^ set(names)
+
+
+def test_header_cites_reference_interfaces():
+    src = open(os.path.join(ROOT, "include", "dabgpu.h")).read()
+    for ref in ("ofdm_demodulator.h:109-141", "dab_viterbi_decoder.h:22-33", "fic_decoder.cpp:53-117", "msc_decoder.cpp:46-154",
+                "aac_frame_processor.cpp:126-362", "reed_solomon_decoder.h:18-26"):
+        assert ref in src
+
+
+def test_params_and_errors_without_gpu(dab):
+    p = dab.get_params(1)
+    assert (p.nb_frame_bits, p.nb_fic_bits, p.nb_cif_bits, p.nb_frame_samples) == (230400, 9216, 55296, 196608)
+    assert dab.get_params(3).nb_fib_group_bits == 3072
+    with pytest.raises(dab.DabGpuError) as e:
+        dab.get_params(5)                       # "Invalid transmission mode" (dab_ofdm_params_ref.cpp:53-54)
+    assert e.value.code == dab.ERR_INVALID and "Invalid transmission mode" in str(e.value)
+    L = dab.load_library()
+    if L.dabgpu_device_count() == 0:
+        with pytest.raises(dab.DabGpuError) as e2:
+            dab.DabGpu(mode=1)
+        assert e2.value.code == dab.ERR_CUDA and "no CPU fallback" in str(e2.value)
+
+
+def test_product_never_references_the_oracle():
+    """Nothing under the package (the product) may import, link or dlopen anything under oracle/."""
+    pkg = os.path.join(ROOT, "sdrplusplus-dab-radio-plugin_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "pyref" not in txt and "libdaboracle" not in txt and "libdabref" not in txt and "dab_oracle" not in txt, f
+
+
+def _shard_worker(rank, world, port, n_streams, q):
+    import torch.distributed as dist
+    import importlib
+    import torch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shard = importlib.import_module("sdrplusplus-dab-radio-plugin_b200.shard")
+    mine = shard.streams_for_rank(n_streams, rank, world)
+    owned = torch.zeros(n_streams, dtype=torch.int32)
+    owned[mine] = 1
+    dist.all_reduce(owned)                                        # reporting only: the data path has no collective
+    t = torch.tensor([float(len(mine))])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    q.put((rank, owned.tolist(), float(t.item()), len(mine)))
+    dist.destroy_process_group()
+
+
+def test_stream_sharding_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n_streams, world = 1025, 2
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, 29581, n_streams, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, owned, mx, n in res:
+        assert owned == [1] * n_streams          # every stream owned exactly once
+        assert mx == 513
+    assert sorted(r[3] for r in res) == [512, 513]
