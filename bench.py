@@ -43,7 +43,8 @@ def _load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region.  NVML is polled in-process every ~2 ms (an nvidia-smi
+    subprocess takes longer than the whole timed region); falls back to the nvidia-smi line of B200_PROFILING.md."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -52,8 +53,25 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.max_mhz = None
         self.stop_flag = False
+        self.source = "nvml"
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        while not self.stop_flag:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            for n, b in bits.items():
+                if r & b:
+                    self.reasons.add(n)
+            time.sleep(0.002)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -68,11 +86,18 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.15)
+            time.sleep(0.05)
+
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
 
     def summary(self):
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_min_mhz": s[0] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s), "source": self.source}
 
 
 def cpu_reference_ofdm(n_threads: int, frames_per_thread: int, target_seconds: float):
@@ -141,12 +166,12 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ofdm", choices=["ofdm", "full"])
     ap.add_argument("--streams", type=int, default=256)
-    ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -240,41 +265,59 @@ def main():
     # whole-job throughput: samples actually consumed by all ranks / max time (every stream advances one frame per step)
     value = world * S * FRAME_SAMPLES * K / (ms_max * 1e-3) / 1e6
 
-    # ---- end to end through the C ABI with host buffers -----------------------------------------
+    # ---- end to end through the C ABI with HOST buffers: dabgpu_submit / dabgpu_wait, two tickets in flight ----
+    # every step copies that step's u8 IQ from pinned host memory (H2D), runs the kernels and copies the step's
+    # results back (D2H): the soft-bit frames for the OFDM workload, the decoded FIC/MSC bytes for the full chain.
     Ke = min(args.e2e_steps, K)
     n_e = W + Ke + 1
+    P = g.P
     host_iq = torch.empty((S, 2 * n_e * FRAME_SAMPLES), dtype=torch.uint8).pin_memory()
     host_iq.copy_(iq[:, :2 * n_e * FRAME_SAMPLES])
-    host_out = torch.empty((S, g.P.nb_frame_bits), dtype=torch.int8).pin_memory()
-    produced = np.zeros(S, dtype=np.uint8)
+    D = pkg.PIPELINE_DEPTH
+    if full:
+        outs = [dict(msc_host=torch.empty((S, P.nb_cifs, pkg.CIF_OUT_STRIDE), dtype=torch.uint8).pin_memory(),
+                     fic_host=torch.empty((S, P.nb_cifs, pkg.FIC_GROUP_STRIDE), dtype=torch.uint8).pin_memory(),
+                     fic_crc_host=torch.empty((S, P.nb_cifs, 4), dtype=torch.uint8).pin_memory(),
+                     msc_valid_host=torch.empty((S, P.nb_cifs, 64), dtype=torch.uint8).pin_memory(),
+                     chan_status_host=torch.zeros((S, 2), dtype=torch.int32).pin_memory()) for _ in range(D)]
+    else:
+        outs = [dict(frames_host=torch.empty((S, P.nb_frame_bits), dtype=torch.int8).pin_memory(),
+                     produced_host=torch.zeros(S, dtype=torch.uint8).pin_memory()) for _ in range(D)]
+    d2h_bytes = sum(t.numel() * t.element_size() for t in outs[0].values())
     g2 = pkg.DabGpu(mode=1, max_streams=S, device=local_rank, cuda_stream=stream.cuda_stream)
     if full:
         for s in range(S):
             g2.msc_configure(s, subs)
     h_np = host_iq.numpy()
-    out_np = host_out.numpy()
-    import ctypes as C
+    tickets = {}
+    n_prod = 0
 
-    def e2e_step(i):
+    def e2e_submit(i):
+        o = outs[i % D]
         view = h_np[:, 2 * i * FRAME_SAMPLES: 2 * (i + 1) * FRAME_SAMPLES]
-        pkg._check(g2.L.dabgpu_ofdm_process(g2.h, C.c_void_p(view.ctypes.data), h_np.strides[0], 0, S, FRAME_SAMPLES, BLOCK))
-        if full:
-            g2.chan_decode()
-            g2.sync()
-        pkg._check(g2.L.dabgpu_ofdm_fetch_latest(g2.h, 0, S, C.c_void_p(out_np.ctypes.data), C.c_void_p(produced.ctypes.data)))
+        tickets[i] = g2.submit(view.ctypes.data, h_np.strides[0], FRAME_SAMPLES, block_size=BLOCK, run_chan_decode=full,
+                               **{k: v.data_ptr() for k, v in o.items()})
+
+    def e2e_retire(i):
+        g2.wait(tickets.pop(i))
+        o = outs[i % D]
+        return int(o["chan_status_host"][:, 0].sum()) if full else int(o["produced_host"].sum())
 
     for i in range(W):
-        e2e_step(i)
+        e2e_submit(i)
+        e2e_retire(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     e0.record(stream)
-    n_prod = 0
     for i in range(W, W + Ke):
-        e2e_step(i)
-        n_prod += int(produced.sum())
+        if i - D >= W:
+            n_prod += e2e_retire(i - D)
+        e2e_submit(i)
+    for i in range(max(W, W + Ke - D), W + Ke):
+        n_prod += e2e_retire(i)
     e1.record(stream)
     torch.cuda.synchronize()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
@@ -307,8 +350,8 @@ def main():
                    "snr_db": 15, "cfo": "uniform +-20 kHz", "timing": "uniform lead in [0, 196608)"},
         "realtime_streams": value / 2.048,
         "frames_demodulated": frames_all,
-        "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": S * FRAME_SAMPLES * 2, "d2h_bytes_per_step": S * g.P.nb_frame_bits,
-                "steps": Ke, "frames_returned": n_prod},
+        "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": S * FRAME_SAMPLES * 2, "d2h_bytes_per_step": d2h_bytes,
+                "steps": Ke, "frames_returned": n_prod, "api": "dabgpu_submit/dabgpu_wait, 2 tickets in flight, pinned host buffers"},
         "gpu_launches": int(launches),
         "kernel_ms": {k: v["ms"] for k, v in prof.items()},
         "roofline": roofline,

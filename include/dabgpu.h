@@ -144,6 +144,37 @@ DABGPU_API int dabgpu_ofdm_pop_frames(dabgpu_ctx* ctx, int stream, int8_t* frame
 DABGPU_API int dabgpu_ofdm_fetch_latest(dabgpu_ctx* ctx, int first_stream, int n_streams, int8_t* frames_host,
                                         uint8_t* produced);
 
+/* Pipelined variant for throughput hosts (SURVEY.md section 7 "hard part 5": pinned, double-buffered staging).
+ * dabgpu_submit queues, without blocking, (1) the host->device copy of n_samples per stream on a copy stream,
+ * (2) the OFDM kernels and, if run_chan_decode != 0, the channel decode of the frames they produce on the compute
+ * stream, (3) the device->host copy of whatever result pointers are non-NULL on a third stream.  dabgpu_wait blocks
+ * until the results of that ticket are in host memory.  At most DABGPU_PIPELINE_DEPTH tickets are in flight: submit
+ * waits for the oldest one when the pipeline is full.  Host buffers should be pinned (cudaHostAlloc / cudaHostRegister)
+ * for the copies to overlap; they must stay valid until the ticket was waited for.  The reference analogue is the
+ * reader thread / pipeline thread split of OFDM_Demod (ofdm/ofdm_demodulator_threads.h) plus the ThreadedRingBuffer
+ * between OFDM_Demod and BasicRadio (src/radio_block.cpp:20-44). */
+#define DABGPU_PIPELINE_DEPTH 2
+#define DABGPU_CIF_OUT_STRIDE 6912   /* decoded bytes of one CIF never exceed 55296/8 */
+#define DABGPU_FIC_GROUP_STRIDE 128
+typedef struct {
+    const void* iq_host;        /* stream i at iq_host + i*iq_stride_bytes */
+    size_t iq_stride_bytes;
+    int first_stream, n_streams, n_samples, block_size;
+    int run_chan_decode;
+    /* optional outputs (NULL = not copied) */
+    int8_t* frames_host;        /* [n_streams][nb_frame_bits] newest soft-bit frame of each stream */
+    uint8_t* produced_host;     /* [n_streams] 1 if the stream produced a frame in this step */
+    uint8_t* msc_host;          /* [n_streams][nb_cifs][DABGPU_CIF_OUT_STRIDE] decoded sub-channel bytes (offsets: dabgpu_msc_get_layout) */
+    uint8_t* msc_valid_host;    /* [n_streams][nb_cifs][max_subchannels] */
+    uint8_t* fic_host;          /* [n_streams][nb_cifs][DABGPU_FIC_GROUP_STRIDE] */
+    uint8_t* fic_crc_host;      /* [n_streams][nb_cifs][4] */
+    int32_t* chan_status_host;  /* [n_streams][2] = {decoded, frame_index} */
+} dabgpu_step;
+DABGPU_API int dabgpu_submit(dabgpu_ctx* ctx, const dabgpu_step* step, uint64_t* ticket);
+DABGPU_API int dabgpu_wait(dabgpu_ctx* ctx, uint64_t ticket);
+/* byte offset and length of sub-channel sub_index inside one CIF row of the msc_host arena */
+DABGPU_API int dabgpu_msc_get_layout(dabgpu_ctx* ctx, int stream, int sub_index, int* offset, int* bytes_per_cif);
+
 /* ---------------------------------------------------------------------------------------------
  * Viterbi.  Replaces DAB_Viterbi_Decoder::{reset,update,chainback}
  * (dab/algorithms/dab_viterbi_decoder.h:22-33; decoder selected at dab_viterbi_decoder.cpp:51-73 =

@@ -79,6 +79,16 @@ class Profile(C.Structure):
     _fields_ = [("ms", C.c_double * 5), ("launches", C.c_uint64 * 5)]
 
 
+class Step(C.Structure):
+    """dabgpu_step (include/dabgpu.h): one pipelined push of IQ with optional result pointers."""
+    _fields_ = [("iq_host", C.c_void_p), ("iq_stride_bytes", C.c_size_t), ("first_stream", C.c_int), ("n_streams", C.c_int),
+                ("n_samples", C.c_int), ("block_size", C.c_int), ("run_chan_decode", C.c_int), ("frames_host", C.c_void_p),
+                ("produced_host", C.c_void_p), ("msc_host", C.c_void_p), ("msc_valid_host", C.c_void_p), ("fic_host", C.c_void_p),
+                ("fic_crc_host", C.c_void_p), ("chan_status_host", C.c_void_p)]
+
+
+CIF_OUT_STRIDE, FIC_GROUP_STRIDE, PIPELINE_DEPTH = 6912, 128, 2
+
 PROF_CLASSES = ("ofdm_ctl", "ofdm_demod", "viterbi", "dabplus", "chan_misc")
 
 EXPORTS = [
@@ -88,7 +98,7 @@ EXPORTS = [
     "dabgpu_ofdm_attach_device_input", "dabgpu_ofdm_advance", "dabgpu_ofdm_get_status", "dabgpu_ofdm_pop_frames",
     "dabgpu_ofdm_fetch_latest", "dabgpu_viterbi_decode", "dabgpu_msc_configure", "dabgpu_softbits_push", "dabgpu_chan_decode",
     "dabgpu_chan_get_status", "dabgpu_chan_get_fic", "dabgpu_chan_get_msc", "dabgpu_chan_get_dabplus_events", "dabgpu_rs_decode",
-    "dabgpu_get_counters",
+    "dabgpu_get_counters", "dabgpu_submit", "dabgpu_wait", "dabgpu_msc_get_layout",
 ]
 
 _lib = None
@@ -134,6 +144,9 @@ def load_library() -> C.CDLL:
     L.dabgpu_chan_get_dabplus_events.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.dabgpu_rs_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.dabgpu_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+    L.dabgpu_submit.argtypes = [C.c_void_p, C.POINTER(Step), C.POINTER(C.c_uint64)]
+    L.dabgpu_wait.argtypes = [C.c_void_p, C.c_uint64]
+    L.dabgpu_msc_get_layout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -313,6 +326,29 @@ class DabGpu:
     def ofdm_advance(self, n_samples: int, block_size: int = 65536, first_stream: int = 0, n_streams: Optional[int] = None):
         _check(self.L.dabgpu_ofdm_advance(self.h, first_stream, self.max_streams - first_stream if n_streams is None else n_streams,
                                           n_samples, block_size))
+
+    def submit(self, iq_ptr: int, iq_stride_bytes: int, n_samples: int, block_size: int = 65536, first_stream: int = 0,
+               n_streams: Optional[int] = None, run_chan_decode: bool = False, **out_ptrs) -> int:
+        """dabgpu_submit: queue H2D + OFDM (+ channel decode) + D2H without blocking; returns the ticket.
+        out_ptrs: frames_host, produced_host, msc_host, msc_valid_host, fic_host, fic_crc_host, chan_status_host (raw addresses)."""
+        st = Step()
+        st.iq_host, st.iq_stride_bytes = iq_ptr, iq_stride_bytes
+        st.first_stream = first_stream
+        st.n_streams = self.max_streams - first_stream if n_streams is None else n_streams
+        st.n_samples, st.block_size, st.run_chan_decode = n_samples, block_size, int(run_chan_decode)
+        for k, v in out_ptrs.items():
+            setattr(st, k, v)
+        t = C.c_uint64(0)
+        _check(self.L.dabgpu_submit(self.h, C.byref(st), C.byref(t)))
+        return int(t.value)
+
+    def wait(self, ticket: int) -> None:
+        _check(self.L.dabgpu_wait(self.h, ticket))
+
+    def msc_layout(self, stream: int, sub_index: int) -> Tuple[int, int]:
+        off, nb = C.c_int(0), C.c_int(0)
+        _check(self.L.dabgpu_msc_get_layout(self.h, stream, sub_index, C.byref(off), C.byref(nb)))
+        return off.value, nb.value
 
     def ofdm_status(self, stream: int) -> dict:
         st = OfdmStatus()

@@ -4,7 +4,7 @@
 #include "viterbi.cuh"
 #include "chan.cuh"
 #include "dabplus.cuh"
-#include "ofdm.cuh"
+#include "ofdm_host.cuh"
 
 #define DABGPU_VERSION "dabgpu 0.1 (sm_100a)"
 
@@ -45,6 +45,17 @@ struct dabgpu_ctx {
 
     // OFDM
     OfdmState ofdm;
+
+    // dabgpu_submit / dabgpu_wait pipeline
+    struct PipeSlot {
+        cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+        DevBuf d_stage, d_produced;
+        uint64_t ticket = 0;
+        bool busy = false;
+    } pipe[DABGPU_PIPELINE_DEPTH];
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    uint64_t next_ticket = 1;
+    size_t pipe_recent_samples[DABGPU_PIPELINE_DEPTH] = {0, 0};
 };
 
 static bool is_pow2(size_t v) { return v && !(v & (v - 1)); }
@@ -226,6 +237,15 @@ void dabgpu_ctx_destroy(dabgpu_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->prof.destroy();
+    for (auto& sl : ctx->pipe) {
+        if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+        if (sl.compute_done) cudaEventDestroy(sl.compute_done);
+        if (sl.d2h_done) cudaEventDestroy(sl.d2h_done);
+        sl.d_stage.release();
+        sl.d_produced.release();
+    }
+    if (ctx->s_h2d) { cudaStreamSynchronize(ctx->s_h2d); cudaStreamDestroy(ctx->s_h2d); }
+    if (ctx->s_d2h) { cudaStreamSynchronize(ctx->s_d2h); cudaStreamDestroy(ctx->s_d2h); }
     ofdm_destroy(ctx->ofdm);
     dabplus_destroy(ctx->dabplus);
     DevBuf* bufs[] = {&ctx->d_prbs, &ctx->d_counter, &ctx->d_scratch, &ctx->d_jobs, &ctx->d_vsoft, &ctx->d_vout, &ctx->d_verr,
@@ -618,6 +638,98 @@ int dabgpu_ofdm_fetch_latest(dabgpu_ctx* ctx, int first, int n, int8_t* frames_h
     if (!frames_host || !produced) return set_error(DABGPU_ERR_INVALID, "null output");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     return ofdm_fetch_latest(ctx->ofdm, first, n, frames_host, produced, ctx->stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pipelined step: H2D (copy stream) -> OFDM [+ channel decode] (compute stream) -> D2H (copy-out stream)
+// ---------------------------------------------------------------------------------------------
+static int pipe_init(dabgpu_ctx* ctx) {
+    if (ctx->s_h2d) return DABGPU_OK;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    for (auto& sl : ctx->pipe) {
+        CUDA_TRY(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
+    }
+    return DABGPU_OK;
+}
+
+int dabgpu_submit(dabgpu_ctx* ctx, const dabgpu_step* st, uint64_t* ticket) {
+    if (!ctx || !st || !ticket) return set_error(DABGPU_ERR_INVALID, "null argument");
+    int rc = check_stream_range(ctx, st->first_stream, st->n_streams);
+    if (rc) return rc;
+    if (!st->iq_host || st->n_samples <= 0 || st->n_streams == 0) return set_error(DABGPU_ERR_INVALID, "bad IQ buffer");
+    OfdmState& O = ctx->ofdm;
+    if (O.external_ring) return set_error(DABGPU_ERR_STATE, "a device input buffer is attached: use dabgpu_ofdm_advance");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    if ((rc = pipe_init(ctx))) return rc;
+    const uint64_t t = ctx->next_ticket;
+    auto& sl = ctx->pipe[t % DABGPU_PIPELINE_DEPTH];
+    auto& prev = ctx->pipe[(t + DABGPU_PIPELINE_DEPTH - 1) % DABGPU_PIPELINE_DEPTH];
+    // the copy of this step overlaps the compute of the previous one: together they must fit the ring headroom
+    const size_t prev_samples = ctx->pipe_recent_samples[(t + DABGPU_PIPELINE_DEPTH - 1) % DABGPU_PIPELINE_DEPTH];
+    if (size_t(st->n_samples) + prev_samples > ofdm_ring_headroom(O))
+        return set_error(DABGPU_ERR_INVALID, "n_samples %d (+%zu in flight) exceeds the IQ ring headroom %zu: raise ring_samples", st->n_samples,
+                         prev_samples, ofdm_ring_headroom(O));
+    if (sl.busy) { CUDA_TRY(cudaEventSynchronize(sl.d2h_done)); sl.busy = false; }
+    const int n = st->n_streams, first = st->first_stream;
+    const size_t fb = size_t(ctx->P.nb_frame_bits);
+    // (1) copy in; the ring region being overwritten was last read by the compute two tickets ago, which d2h_done covers
+    if (prev.busy) CUDA_TRY(cudaStreamWaitEvent(ctx->s_h2d, prev.h2d_done, 0));
+    if ((rc = ofdm_upload(O, st->iq_host, st->iq_stride_bytes, first, n, 0, size_t(st->n_samples), ctx->s_h2d))) return rc;
+    CUDA_TRY(cudaEventRecord(sl.h2d_done, ctx->s_h2d));
+    // (2) compute
+    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0));
+    const int bs = st->block_size > 0 ? st->block_size : st->n_samples;
+    if ((rc = ofdm_run(O, first, n, st->n_samples, bs, ctx->stream))) return rc;
+    if (st->frames_host || st->produced_host) {
+        if ((rc = sl.d_stage.alloc(size_t(n) * fb))) return rc;
+        if ((rc = sl.d_produced.alloc(size_t(n)))) return rc;
+        if ((rc = ofdm_gather_latest(O, first, n, sl.d_stage.as<int8_t>(), sl.d_produced.as<uint8_t>(), ctx->stream))) return rc;
+    }
+    if (st->run_chan_decode && (rc = dabgpu_chan_decode(ctx, first, n))) return rc;
+    CUDA_TRY(cudaEventRecord(sl.compute_done, ctx->stream));
+    // (3) copy out.  The next compute may overwrite the channel-decode arenas: it is made to wait for this copy.
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_d2h, sl.compute_done, 0));
+    const int nb_cifs = ctx->P.nb_cifs;
+    if (st->frames_host) CUDA_TRY(cudaMemcpyAsync(st->frames_host, sl.d_stage.p, size_t(n) * fb, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    if (st->produced_host) CUDA_TRY(cudaMemcpyAsync(st->produced_host, sl.d_produced.p, size_t(n), cudaMemcpyDeviceToHost, ctx->s_d2h));
+    bool arenas = false;
+    if (st->msc_host) { arenas = true; CUDA_TRY(cudaMemcpyAsync(st->msc_host, ctx->d_msc_out.as<uint8_t>() + size_t(first) * nb_cifs * CIF_OUT_STRIDE, size_t(n) * nb_cifs * CIF_OUT_STRIDE, cudaMemcpyDeviceToHost, ctx->s_d2h)); }
+    if (st->msc_valid_host) { arenas = true; CUDA_TRY(cudaMemcpyAsync(st->msc_valid_host, ctx->d_msc_valid.as<uint8_t>() + size_t(first) * nb_cifs * ctx->max_subs, size_t(n) * nb_cifs * ctx->max_subs, cudaMemcpyDeviceToHost, ctx->s_d2h)); }
+    if (st->fic_host) { arenas = true; CUDA_TRY(cudaMemcpyAsync(st->fic_host, ctx->d_fic_out.as<uint8_t>() + size_t(first) * nb_cifs * FIC_GROUP_BYTES, size_t(n) * nb_cifs * FIC_GROUP_BYTES, cudaMemcpyDeviceToHost, ctx->s_d2h)); }
+    if (st->fic_crc_host) { arenas = true; CUDA_TRY(cudaMemcpyAsync(st->fic_crc_host, ctx->d_fic_crc.as<uint8_t>() + size_t(first) * nb_cifs * 4, size_t(n) * nb_cifs * 4, cudaMemcpyDeviceToHost, ctx->s_d2h)); }
+    if (st->chan_status_host) { arenas = true; CUDA_TRY(cudaMemcpyAsync(st->chan_status_host, ctx->d_status.as<int32_t>() + 2 * size_t(first), size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->s_d2h)); }
+    CUDA_TRY(cudaEventRecord(sl.d2h_done, ctx->s_d2h));
+    if (arenas) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, sl.d2h_done, 0));
+    sl.busy = true;
+    sl.ticket = t;
+    ctx->pipe_recent_samples[t % DABGPU_PIPELINE_DEPTH] = size_t(st->n_samples);
+    ctx->next_ticket = t + 1;
+    *ticket = t;
+    return DABGPU_OK;
+}
+
+int dabgpu_wait(dabgpu_ctx* ctx, uint64_t ticket) {
+    if (!ctx) return set_error(DABGPU_ERR_INVALID, "null context");
+    if (ticket == 0 || ticket >= ctx->next_ticket) return set_error(DABGPU_ERR_INVALID, "unknown ticket %llu", (unsigned long long)ticket);
+    auto& sl = ctx->pipe[ticket % DABGPU_PIPELINE_DEPTH];
+    if (!sl.busy || sl.ticket != ticket) return DABGPU_OK;   // already retired
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaEventSynchronize(sl.d2h_done));
+    sl.busy = false;
+    return DABGPU_OK;
+}
+
+int dabgpu_msc_get_layout(dabgpu_ctx* ctx, int stream, int sub_index, int* offset, int* bytes_per_cif) {
+    int rc = check_stream_range(ctx, stream, 1);
+    if (rc) return rc;
+    const auto& hs = ctx->subs[size_t(stream)];
+    if (sub_index < 0 || size_t(sub_index) >= hs.size()) return set_error(DABGPU_ERR_INVALID, "sub-channel index %d not configured", sub_index);
+    if (offset) *offset = int(hs[size_t(sub_index)].out_offset);
+    if (bytes_per_cif) *bytes_per_cif = int(hs[size_t(sub_index)].n_out_bytes);
+    return DABGPU_OK;
 }
 
 }  // extern "C"

@@ -40,6 +40,8 @@ struct OfdmStream {
     float frame_f;            // coarse+fine sampled when the frame was handed over (ofdm_demodulator.cpp:672)
     int32_t block_size;
     int32_t produced_last;    // frames emitted during the last process/advance call
+    int32_t corr_contig;      // the correlation buffer holds consecutive ring samples ending at `consumed` (steady state)
+    int32_t head_contig;      // the frame being assembled is contiguous in the ring from frame_ring_base - n_head
     int32_t pad0;
     unsigned long long consumed, push_end, block_end, frame_ring_base;
 };
@@ -68,6 +70,8 @@ struct OfdmDev {
     const float2* prs_time_ref;  // conj(IFFT(relative phase of PRS)), natural order
     const uint16_t* dpos;        // padded smem position of natural index k after the in-place DIF FFT
     const uint16_t* outpos;      // padded smem position of the carrier that feeds output bit i (frequency de-interleaver)
+    const uint16_t* obin;        // demod kernel: [N] output index (0..K-1) of the bin at FFT-output position a, 0xFFFF = unused bin
+    int tma_ok;                  // ring base/stride/capacity are multiples of 16 bytes: TMA bulk staging may be used
     // outputs
     int8_t* frames;              // [stream][slot][frame_bits]
     uint32_t* frames_written;    // [stream]
@@ -224,104 +228,6 @@ __device__ __forceinline__ float2 ofdm_frame_sample(const OfdmDev& D, const int 
     return ofdm_ring_sample(D, s, st.frame_ring_base + (k - st.n_head));
 }
 
-template <int N>
-__global__ void __launch_bounds__(N / 8, (N == 2048) ? 3 : 4)
-k_ofdm_demod(const OfdmDev D, const int first_stream) {
-    constexpr int NT = N / 8;
-    constexpr int NP = N + N / 8;      // padded length
-    __shared__ float s_re[2][NP];
-    __shared__ float s_im[2][NP];
-    __shared__ float2 s_cp[N / 4];
-    __shared__ float2 s_part[NT / 32 > 0 ? NT / 32 : 1];
-
-    const int s = first_stream + blockIdx.y;
-    const OfdmStream st = D.st[s];
-    if (st.pending != 1) return;
-    const OfdmGeom& g = D.g;
-    const int tid = threadIdx.x;
-    const int l0 = blockIdx.x * g.sym_per_chunk;
-    if (l0 >= g.L - 1) return;
-    const int l1 = min(l0 + g.sym_per_chunk, g.L - 1);
-    const float f = st.frame_f;
-    const float2* head = D.head + size_t(s) * (g.Tsym + g.CP);
-    const uint32_t slot = D.frames_written[s] & D.slot_mask;
-    int8_t* out_frame = D.frames + (size_t(s) * (D.slot_mask + 1u) + slot) * g.frame_bits;
-    const int CP = g.CP, K = g.K;
-
-    for (int l = l0; l <= l1; l++) {
-        float* re = s_re[l & 1];
-        float* im = s_im[l & 1];
-        const bool own = (l < l1) || (l == g.L - 1);   // this CTA accounts for the symbol's cyclic-prefix phase
-        const float dt0 = __fmul_rn(float(l * g.Tsym), f);
-        const uint32_t sym_base = uint32_t(l) * uint32_t(g.Tsym);
-        float2 x[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int n = CP + tid + j * NT;
-            x[j] = pll_rotate(ofdm_frame_sample(D, s, st, sym_base + n, head), n, f, dt0);
-        }
-        __syncthreads();   // previous iteration's DQPSK reads of buffer (l&1) and of s_cp are complete
-        if (own) {
-#pragma unroll
-            for (int m = 0; m < 2; m++) {
-                const int n = tid + m * NT;
-                if (n < CP) s_cp[n] = pll_rotate(ofdm_frame_sample(D, s, st, sym_base + n, head), n, f, dt0);
-            }
-            __syncthreads();
-            // sum over n < CP of sym[N+n] * conj(sym[n])   (ofdm_demodulator.cpp:768-777)
-            float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int b = tid + j * NT;
-                if (b >= N - CP) {
-                    const float2 c = s_cp[b - (N - CP)];
-                    acc.x += __fmaf_rn(x[j].y, c.y, x[j].x * c.x);
-                    acc.y += __fmaf_rn(x[j].y, c.x, -(x[j].x * c.y));
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                acc.x += __shfl_xor_sync(FULL_MASK, acc.x, o);
-                acc.y += __shfl_xor_sync(FULL_MASK, acc.y, o);
-            }
-            if ((tid & 31) == 0) s_part[tid >> 5] = acc;
-        }
-        fft_cta<N, false>(x, re, im, D.tw, tid);
-        __syncthreads();
-        if (own && tid == 0) {
-            float2 t = make_float2(0.0f, 0.0f);
-            for (int w = 0; w < NT / 32; w++) { t.x += s_part[w].x; t.y += s_part[w].y; }
-            D.phase_err[size_t(s) * g.L + l] = atan2f(t.y, t.x);
-        }
-        if (l > l0) {
-            // DQPSK X_{l-1} * conj(X_l), frequency de-interleave, L-infinity normalise, truncate to int8
-            // (ofdm_demodulator.cpp:842-889; bit0 = trunc(-127*re/A), bit1 = trunc(+127*im/A))
-            const float* pre = s_re[(l - 1) & 1];
-            const float* pim = s_im[(l - 1) & 1];
-            int8_t* row = out_frame + size_t(l - 1) * 2u * K;
-            for (int u = tid; u < K / 4; u += NT) {
-                const ushort4 p4 = __ldg(reinterpret_cast<const ushort4*>(D.outpos) + u);
-                const unsigned short pp[4] = {p4.x, p4.y, p4.z, p4.w};
-                uint32_t w0 = 0, w1 = 0;
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const int p = pp[e];
-                    const float ar = pre[p], ai = pim[p], br = re[p], bi = im[p];
-                    const float vr = ar * br + ai * bi;
-                    const float vi = ai * br - ar * bi;
-                    const float A = fmaxf(fabsf(vr), fabsf(vi));
-                    const int q0 = int(__fmul_rn(__fdiv_rn(vr, A), -127.0f));
-                    const int q1 = int(__fmul_rn(__fdiv_rn(vi, A), 127.0f));
-                    w0 |= uint32_t(uint8_t(q0)) << (8 * e);
-                    w1 |= uint32_t(uint8_t(q1)) << (8 * e);
-                }
-                *reinterpret_cast<uint32_t*>(row + 4 * u) = w0;
-                *reinterpret_cast<uint32_t*>(row + K + 4 * u) = w1;
-            }
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Control kernel: one CTA (N/8 threads) per stream walks the reference state machine over the
 // newly available samples; heavy per-frame work is left to k_ofdm_demod.
@@ -349,18 +255,31 @@ __device__ __forceinline__ void ctl_reset(OfdmStream& st) {   // OFDM_Demod::Res
     st.coarse = 0.0f;
     st.fine = 0.0f;
     st.fine_time_offset = 0;
+    st.corr_contig = 0;
 }
 
-// mean of |re|+|im| over `count` samples starting at abs index a0, computed by one warp (CalculateL1Average :922-932)
-__device__ __forceinline__ float ctl_l1_window(const OfdmDev& D, const int s, const unsigned long long a0, const int count, const int lane) {
-    float acc = 0.0f;
-    for (int i = lane; i < count; i += 32) {
-        const float2 v = ofdm_ring_sample(D, s, a0 + i);
-        acc += fabsf(v.x) + fabsf(v.y);
+// CalculateL1Average (:922-932) for a batch of windows: window w (< nb) covers `count` samples from a0 + w*stride.
+// Two adjacent lanes share a window so that a CTA of NT threads has NT/2 windows and all their loads in flight at
+// once (the control kernel is latency bound: one dependent global round trip per batch instead of one per window).
+template <int NT>
+__device__ __forceinline__ void ctl_l1_batch(const OfdmDev& D, const int s, const unsigned long long a0, const int stride, const int count,
+                                             const int nb, float* __restrict__ out, const int tid) {
+    const int half = (count + 1) >> 1;
+    for (int w0 = 0; w0 < nb; w0 += NT / 2) {
+        const int w = w0 + (tid >> 1);
+        float acc = 0.0f;
+        if (w < nb) {
+            const int i0 = (tid & 1) * half, i1 = min(count, i0 + half);
+            const unsigned long long base = a0 + (unsigned long long)w * (unsigned long long)stride;
+#pragma unroll 10
+            for (int i = i0; i < i1; i++) {
+                const float2 v = ofdm_ring_sample(D, s, base + i);
+                acc += fabsf(v.x) + fabsf(v.y);
+            }
+        }
+        acc += __shfl_xor_sync(FULL_MASK, acc, 1);
+        if (w < nb && (tid & 1) == 0) out[w] = acc / float(count);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, o);
-    return acc / float(count);
 }
 
 template <int N>
@@ -421,10 +340,7 @@ k_ofdm_ctl(const OfdmDev D, const int first_stream, const int n_new_samples, con
                 const int n_win = (M + Lstep - 1) / Lstep;
                 for (int w0 = 0; w0 < n_win; w0 += OFDM_L1_BATCH) {
                     const int nb = min(OFDM_L1_BATCH, n_win - w0);
-                    for (int w = warp; w < nb; w += NW) {
-                        const float v = ctl_l1_window(D, s, bstart + (unsigned long long)(w0 + w) * Lstep, K1, lane);
-                        if (lane == 0) sh.l1[w] = v;
-                    }
+                    ctl_l1_batch<NT>(D, s, bstart + (unsigned long long)w0 * Lstep, Lstep, K1, nb, sh.l1, tid);
                     __syncthreads();
                     if (tid == 0) {
                         const float beta = D.cfg.signal_l1_update_beta;
@@ -450,10 +366,7 @@ k_ofdm_ctl(const OfdmDev D, const int first_stream, const int n_new_samples, con
             __syncthreads();
             for (int w0 = 0; w0 < n_win; w0 += OFDM_L1_BATCH) {
                 const int nb = min(OFDM_L1_BATCH, n_win - w0);
-                for (int w = warp; w < nb; w += NW) {
-                    const float v = ctl_l1_window(D, s, st.consumed + (unsigned long long)(w0 + w) * K1, K1, lane);
-                    if (lane == 0) sh.l1[w] = v;
-                }
+                ctl_l1_batch<NT>(D, s, st.consumed + (unsigned long long)w0 * K1, K1, K1, nb, sh.l1, tid);
                 __syncthreads();
                 if (tid == 0) {
                     for (int w = 0; w < nb; w++) {
@@ -487,6 +400,7 @@ k_ofdm_ctl(const OfdmDev D, const int first_stream, const int n_new_samples, con
                 if (tid == 0) {
                     st.null_start_found = 0; st.null_end_found = 0;
                     st.corr_len = Lr; st.ring_len = 0;
+                    st.corr_contig = 0;   // CircularBuffer read-out order is not guaranteed to be stream order (circular_buffer.h)
                     st.state = OST_READING_NULL_PRS;
                 }
             }
@@ -663,6 +577,7 @@ k_ofdm_ctl(const OfdmDev D, const int first_stream, const int n_new_samples, con
                 if (tid == 0) {
                     st.frame_fill = st.n_head;
                     st.frame_ring_base = st.consumed;
+                    st.head_contig = st.corr_contig;
                     st.corr_len = 0;
                     st.state = OST_READING_SYMBOLS;
                 }
@@ -681,6 +596,7 @@ k_ofdm_ctl(const OfdmDev D, const int first_stream, const int n_new_samples, con
                 st.consumed += (unsigned long long)take;
                 if (take == need) {
                     st.corr_len = uint32_t(g.Tnull);
+                    st.corr_contig = 1;   // NULL symbol taken from the ring right before `consumed`; READ_NULL_PRS appends what follows
                     st.state = OST_READING_NULL_PRS;
                     st.frame_f = st.coarse + st.fine;
                     st.pending = 1;
@@ -720,317 +636,3 @@ __global__ void k_ofdm_reset(const OfdmDev D, const int stream, const int n_stre
     D.st[s] = st;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Host side
-// ---------------------------------------------------------------------------------------------
-struct OfdmState {
-    uint64_t launches = 0;
-    Profiler* prof = nullptr;
-    OfdmDev dev;
-    dabgpu_params P;
-    int max_streams = 0, frame_slots = 0;
-    size_t ring_cap = 0;          // internal ring capacity (samples)
-    bool external_ring = false;
-    int bps = 2;
-    DevBuf d_ring, d_st, d_null_ring, d_corr, d_head, d_phase, d_tw, d_prs_conj, d_prs_time, d_dpos, d_outpos, d_stage, d_produced;
-    PinnedBuf h_produced;
-    std::vector<unsigned long long> h_written;   // absolute samples written per stream (internal ring)
-};
-
-// PRS phases, EN 300 401 clause 14.3.2 tables 23/24 (reference: dab_prs_ref.cpp:24-194).
-// per block of 32 carriers: (i << 2) | n ; negative carriers first
-static const uint8_t kPrsH[4][32] = {
-    {0, 2, 0, 0, 0, 0, 1, 1, 2, 0, 0, 0, 2, 2, 1, 1, 0, 2, 0, 0, 0, 0, 1, 1, 2, 0, 0, 0, 2, 2, 1, 1},
-    {0, 3, 2, 3, 0, 1, 3, 0, 2, 1, 2, 3, 2, 3, 3, 0, 0, 3, 2, 3, 0, 1, 3, 0, 2, 1, 2, 3, 2, 3, 3, 0},
-    {0, 0, 0, 2, 0, 2, 1, 3, 2, 2, 0, 2, 2, 0, 1, 3, 0, 0, 0, 2, 0, 2, 1, 3, 2, 2, 0, 2, 2, 0, 1, 3},
-    {0, 1, 2, 1, 0, 3, 3, 2, 2, 3, 2, 1, 2, 1, 3, 2, 0, 1, 2, 1, 0, 3, 3, 2, 2, 3, 2, 1, 2, 1, 3, 2},
-};
-static const uint8_t kPrsBlocks1[48] = {1, 6, 8, 13, 3, 6, 10, 15, 2, 5, 10, 15, 1, 6, 11, 15, 2, 6, 10, 13, 1, 7, 9, 14,
-                                        3, 13, 9, 5, 2, 14, 9, 4, 2, 14, 11, 7, 0, 14, 9, 7, 3, 15, 11, 4, 3, 12, 9, 5};
-static const uint8_t kPrsBlocks2[12] = {2, 7, 10, 14, 1, 6, 8, 6, 2, 13, 8, 7};
-static const uint8_t kPrsBlocks3[6] = {2, 7, 8, 14, 10, 6};
-static const uint8_t kPrsBlocks4[24] = {0, 5, 9, 14, 2, 6, 8, 15, 3, 5, 11, 14, 0, 13, 8, 6, 0, 13, 10, 6, 2, 13, 11, 4};
-
-static void host_prs_spectrum(int mode, int N, int K, std::vector<float2>& prs) {
-    const uint8_t* tab = (mode == 1) ? kPrsBlocks1 : (mode == 2) ? kPrsBlocks2 : (mode == 3) ? kPrsBlocks3 : kPrsBlocks4;
-    prs.assign(size_t(N), make_float2(0.0f, 0.0f));
-    for (int slot = 0; slot < K; slot++) {
-        const int k = (slot < K / 2) ? (slot - K / 2) : (slot - K / 2 + 1);
-        const int i = tab[slot / 32] >> 2, n = tab[slot / 32] & 3;
-        const float phi = float(M_PI) / 2.0f * float(kPrsH[i][slot % 32] + n);
-        prs[size_t(k < 0 ? N + k : k)] = make_float2(cosf(phi), sinf(phi));
-    }
-}
-
-static void host_dft_double(std::vector<double>& re, std::vector<double>& im, bool inverse) {
-    // simple recursive-free radix-2 on doubles for table generation only
-    const size_t n = re.size();
-    for (size_t i = 1, j = 0; i < n; i++) {
-        size_t bit = n >> 1;
-        for (; j & bit; bit >>= 1) j ^= bit;
-        j ^= bit;
-        if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
-    }
-    for (size_t len = 2; len <= n; len <<= 1) {
-        const double ang = (inverse ? 2.0 : -2.0) * M_PI / double(len);
-        for (size_t i = 0; i < n; i += len)
-            for (size_t k = 0; k < len / 2; k++) {
-                const double wr = cos(ang * double(k)), wi = sin(ang * double(k));
-                const double ur = re[i + k], ui = im[i + k];
-                const double vr = re[i + k + len / 2] * wr - im[i + k + len / 2] * wi;
-                const double vi = re[i + k + len / 2] * wi + im[i + k + len / 2] * wr;
-                re[i + k] = ur + vr; im[i + k] = ui + vi;
-                re[i + k + len / 2] = ur - vr; im[i + k + len / 2] = ui - vi;
-            }
-    }
-}
-
-static int ofdm_init(OfdmState& O, const dabgpu_config& cfg, const dabgpu_params& P, int frame_slots, int8_t* d_frames,
-                     uint32_t* d_frames_written, dabgpu_frame_info* d_frame_info, unsigned long long* d_counters) {
-    O.P = P;
-    O.max_streams = cfg.max_streams;
-    O.frame_slots = frame_slots;
-    O.bps = (cfg.iq_format == DABGPU_IQ_U8) ? 2 : 8;
-    const int S = cfg.max_streams, N = P.nb_fft, K = P.nb_data_carriers;
-    size_t cap = cfg.ring_samples;
-    if (cap == 0) {
-        cap = 1;
-        while (cap < size_t(P.nb_frame_samples) * 2 + size_t(P.nb_null_period + P.nb_symbol_period)) cap <<= 1;
-    }
-    if (cap & (cap - 1)) return set_error(DABGPU_ERR_INVALID, "ring_samples must be a power of two");
-    if (cap < size_t(P.nb_frame_samples) + size_t(P.nb_null_period + P.nb_symbol_period) + 4096)
-        return set_error(DABGPU_ERR_INVALID, "ring_samples too small for one frame");
-    O.ring_cap = cap;
-    int rc;
-    if ((rc = O.d_ring.alloc(size_t(S) * cap * O.bps))) return rc;
-    if ((rc = O.d_st.alloc(size_t(S) * sizeof(OfdmStream)))) return rc;
-    if ((rc = O.d_null_ring.alloc(size_t(S) * P.nb_null_period * sizeof(float2)))) return rc;
-    if ((rc = O.d_corr.alloc(size_t(S) * (P.nb_null_period + P.nb_symbol_period) * sizeof(float2)))) return rc;
-    if ((rc = O.d_head.alloc(size_t(S) * (P.nb_symbol_period + P.nb_cyclic_prefix) * sizeof(float2)))) return rc;
-    if ((rc = O.d_phase.alloc(size_t(S) * P.nb_frame_symbols * sizeof(float)))) return rc;
-    if ((rc = O.d_produced.alloc(size_t(S)))) return rc;
-    if ((rc = O.h_produced.alloc(size_t(S)))) return rc;
-    cudaMemset(O.d_ring.p, 0, O.d_ring.bytes);
-    cudaMemset(O.d_st.p, 0, O.d_st.bytes);
-    cudaMemset(O.d_null_ring.p, 0, O.d_null_ring.bytes);   // the reference's joint block is zero initialised (joint_allocate.h:21-23)
-    cudaMemset(O.d_corr.p, 0, O.d_corr.bytes);
-    cudaMemset(O.d_head.p, 0, O.d_head.bytes);
-    cudaMemset(O.d_phase.p, 0, O.d_phase.bytes);
-    O.h_written.assign(size_t(S), 0ull);
-
-    // tables
-    std::vector<float2> tw(static_cast<size_t>(N)), prs;
-    for (int n = 0; n < N; n++) {
-        const double a = -2.0 * M_PI * double(n) / double(N);
-        tw[size_t(n)] = make_float2(float(cos(a)), float(sin(a)));
-    }
-    host_prs_spectrum(cfg.transmission_mode, N, K, prs);
-    std::vector<float2> prs_conj(static_cast<size_t>(N)), prs_time(static_cast<size_t>(N));
-    for (int i = 0; i < N; i++) prs_conj[size_t(i)] = make_float2(prs[size_t(i)].x, -prs[size_t(i)].y);
-    {
-        // conj(IFFT(conj(X[i]) * X[i+1]))   (ofdm_demodulator.cpp:136-140)
-        std::vector<double> re(static_cast<size_t>(N), 0.0), im(static_cast<size_t>(N), 0.0);
-        for (int i = 0; i < N - 1; i++) {
-            const double ar = prs[size_t(i)].x, ai = prs[size_t(i)].y, br = prs[size_t(i + 1)].x, bi = prs[size_t(i + 1)].y;
-            re[size_t(i)] = ar * br + ai * bi;
-            im[size_t(i)] = ar * bi - ai * br;
-        }
-        host_dft_double(re, im, true);
-        for (int i = 0; i < N; i++) prs_time[size_t(i)] = make_float2(float(re[size_t(i)]), float(-im[size_t(i)]));
-    }
-    // digit reversal of the in-place DIF (radices 8,8,8,4 / 8,8,8,2 / 8,8,8 / 8,8,4)
-    std::vector<int> radices;
-    switch (N) {
-    case 2048: radices = {8, 8, 8, 4}; break;
-    case 1024: radices = {8, 8, 8, 2}; break;
-    case 512: radices = {8, 8, 8}; break;
-    default: radices = {8, 8, 4}; break;
-    }
-    std::vector<uint16_t> dpos(static_cast<size_t>(N)), outpos(static_cast<size_t>(K));
-    for (int k = 0; k < N; k++) {
-        int a = 0, rem = N, kk = k;
-        for (int R : radices) { const int d = kk % R; kk /= R; rem /= R; a += d * rem; }
-        dpos[size_t(k)] = uint16_t(OFDM_PAD(a));
-    }
-    {
-        // frequency de-interleaver (dab_mapper_ref.cpp:10-50) composed with the carrier -> FFT bin map (ofdm_demodulator.cpp:853-864)
-        std::vector<int> cmap;
-        int v = 0;
-        const int dc = N / 2, lo = dc - K / 2, hi = dc + K / 2;
-        for (int i = 0; i < N; i++) {
-            if (i > 0) v = (13 * v + N / 4 - 1) % N;
-            if (v < lo || v > hi || v == dc) continue;
-            cmap.push_back(v < dc ? v - lo : v - lo - 1);
-        }
-        for (int i = 0; i < K; i++) {
-            const int slot = cmap[size_t(i)];
-            const int kf = (slot < K / 2) ? (slot - K / 2) : (slot - K / 2 + 1);
-            outpos[size_t(i)] = dpos[size_t((N + kf) % N)];
-        }
-    }
-    if ((rc = O.d_tw.alloc(tw.size() * sizeof(float2)))) return rc;
-    if ((rc = O.d_prs_conj.alloc(prs_conj.size() * sizeof(float2)))) return rc;
-    if ((rc = O.d_prs_time.alloc(prs_time.size() * sizeof(float2)))) return rc;
-    if ((rc = O.d_dpos.alloc(dpos.size() * 2))) return rc;
-    if ((rc = O.d_outpos.alloc(outpos.size() * 2))) return rc;
-    cudaMemcpy(O.d_tw.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice);
-    cudaMemcpy(O.d_prs_conj.p, prs_conj.data(), prs_conj.size() * sizeof(float2), cudaMemcpyHostToDevice);
-    cudaMemcpy(O.d_prs_time.p, prs_time.data(), prs_time.size() * sizeof(float2), cudaMemcpyHostToDevice);
-    cudaMemcpy(O.d_dpos.p, dpos.data(), dpos.size() * 2, cudaMemcpyHostToDevice);
-    cudaMemcpy(O.d_outpos.p, outpos.data(), outpos.size() * 2, cudaMemcpyHostToDevice);
-
-    OfdmDev& D = O.dev;
-    D.g.L = P.nb_frame_symbols; D.g.Tsym = P.nb_symbol_period; D.g.Tnull = P.nb_null_period; D.g.CP = P.nb_cyclic_prefix;
-    D.g.N = N; D.g.K = K; D.g.frame_bits = P.nb_frame_bits; D.g.frame_samples = P.nb_frame_samples;
-    D.g.sym_per_chunk = (P.nb_frame_symbols == 153) ? 19 : 15;
-    D.g.n_chunks = (P.nb_frame_symbols - 1 + D.g.sym_per_chunk - 1) / D.g.sym_per_chunk;
-    D.cfg = cfg.ofdm;
-    D.iq_format = cfg.iq_format;
-    D.ring = O.d_ring.as<uint8_t>();
-    D.ring_stride = cap;
-    D.ring_mask = cap - 1;
-    D.st = O.d_st.as<OfdmStream>();
-    D.null_ring = O.d_null_ring.as<float2>();
-    D.corr = O.d_corr.as<float2>();
-    D.head = O.d_head.as<float2>();
-    D.phase_err = O.d_phase.as<float>();
-    D.tw = O.d_tw.as<float2>();
-    D.prs_fft_conj = O.d_prs_conj.as<float2>();
-    D.prs_time_ref = O.d_prs_time.as<float2>();
-    D.dpos = O.d_dpos.as<uint16_t>();
-    D.outpos = O.d_outpos.as<uint16_t>();
-    D.frames = d_frames;
-    D.frames_written = d_frames_written;
-    D.frame_info = d_frame_info;
-    D.slot_mask = uint32_t(frame_slots - 1);
-    D.counters = d_counters;
-    return DABGPU_OK;
-}
-
-static void ofdm_destroy(OfdmState& O) {
-    DevBuf* bufs[] = {&O.d_ring, &O.d_st, &O.d_null_ring, &O.d_corr, &O.d_head, &O.d_phase, &O.d_tw, &O.d_prs_conj, &O.d_prs_time,
-                      &O.d_dpos, &O.d_outpos, &O.d_stage, &O.d_produced};
-    for (DevBuf* b : bufs) b->release();
-    O.h_produced.release();
-}
-
-static int ofdm_reset(OfdmState& O, int stream, cudaStream_t cs) {
-    const int n = (stream < 0) ? O.max_streams : 1;
-    k_ofdm_reset<<<(n + 127) / 128, 128, 0, cs>>>(O.dev, stream, n, 0);
-    O.launches++;
-    CUDA_TRY(cudaGetLastError());
-    return DABGPU_OK;
-}
-
-template <int N>
-static int ofdm_run_t(OfdmState& O, int first, int n, int n_samples, int block_size, cudaStream_t cs) {
-    const int max_frames = n_samples / O.P.nb_frame_samples + 2;
-    const dim3 dgrid(O.dev.g.n_chunks, n);
-    Profiler& pf = *O.prof;
-    for (int it = 0; it < max_frames; it++) {
-        pf.begin(PROF_OFDM_CTL, cs);
-        k_ofdm_ctl<N><<<n, N / 8, 0, cs>>>(O.dev, first, n_samples, block_size, it == 0 ? 1 : 0);
-        pf.end(cs);
-        pf.begin(PROF_OFDM_DEMOD, cs);
-        k_ofdm_demod<N><<<dgrid, N / 8, 0, cs>>>(O.dev, first);
-        pf.end(cs);
-        O.launches += 2;
-    }
-    pf.begin(PROF_OFDM_CTL, cs);
-    k_ofdm_ctl<N><<<n, N / 8, 0, cs>>>(O.dev, first, n_samples, block_size, 0);
-    pf.end(cs);
-    O.launches++;
-    CUDA_TRY(cudaGetLastError());
-    return DABGPU_OK;
-}
-
-static int ofdm_run(OfdmState& O, int first, int n, int n_samples, int block_size, cudaStream_t cs) {
-    if (n == 0 || n_samples == 0) return DABGPU_OK;
-    switch (O.P.nb_fft) {
-    case 2048: return ofdm_run_t<2048>(O, first, n, n_samples, block_size, cs);
-    case 1024: return ofdm_run_t<1024>(O, first, n, n_samples, block_size, cs);
-    case 512: return ofdm_run_t<512>(O, first, n, n_samples, block_size, cs);
-    case 256: return ofdm_run_t<256>(O, first, n, n_samples, block_size, cs);
-    }
-    return set_error(DABGPU_ERR_INVALID, "unsupported FFT size %d", O.P.nb_fft);
-}
-
-static int ofdm_process(OfdmState& O, const void* iq_host, size_t stride_bytes, int first, int n, int n_samples, int block_size, cudaStream_t cs) {
-    if (O.external_ring) return set_error(DABGPU_ERR_STATE, "a device input buffer is attached: use dabgpu_ofdm_advance");
-    // the ring must keep the frame being assembled plus the correlation window: bound the samples per pass
-    const size_t max_chunk = O.ring_cap - size_t(O.P.nb_frame_samples) - size_t(O.P.nb_null_period + O.P.nb_symbol_period) - 1024;
-    const int bs = block_size > 0 ? block_size : n_samples;
-    size_t chunk_max = (max_chunk / size_t(bs)) * size_t(bs);   // keep Process() block boundaries intact
-    if (chunk_max == 0) return set_error(DABGPU_ERR_INVALID, "block_size %d does not fit the IQ ring (%zu samples)", bs, O.ring_cap);
-    const uint8_t* src = static_cast<const uint8_t*>(iq_host);
-    for (size_t done = 0; done < size_t(n_samples);) {
-        const size_t len = std::min(chunk_max, size_t(n_samples) - done);
-        for (int i = 0; i < n; i++) {
-            const int s = first + i;
-            unsigned long long w = O.h_written[size_t(s)];
-            size_t left = len, off = 0;
-            while (left > 0) {
-                const size_t pos = size_t(w & (O.ring_cap - 1));
-                const size_t run = std::min(left, O.ring_cap - pos);
-                CUDA_TRY(cudaMemcpyAsync(O.d_ring.as<uint8_t>() + (size_t(s) * O.ring_cap + pos) * O.bps,
-                                         src + size_t(i) * stride_bytes + (done + off) * O.bps, run * O.bps, cudaMemcpyHostToDevice, cs));
-                w += run; off += run; left -= run;
-            }
-            O.h_written[size_t(s)] = w;
-        }
-        int rc = ofdm_run(O, first, n, int(len), bs, cs);
-        if (rc) return rc;
-        done += len;
-    }
-    CUDA_TRY(cudaStreamSynchronize(cs));
-    return DABGPU_OK;
-}
-
-static int ofdm_attach(OfdmState& O, const void* d_iq, size_t stride_samples, size_t capacity, cudaStream_t cs) {
-    CUDA_TRY(cudaStreamSynchronize(cs));
-    O.dev.ring = static_cast<const uint8_t*>(d_iq);
-    O.dev.ring_stride = stride_samples;
-    O.dev.ring_mask = (capacity & (capacity - 1)) == 0 ? (unsigned long long)(capacity - 1) : ~0ull;
-    O.external_ring = true;
-    k_ofdm_reset<<<(O.max_streams + 127) / 128, 128, 0, cs>>>(O.dev, -1, O.max_streams, 1);
-    O.launches++;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(cs));
-    return DABGPU_OK;
-}
-
-static int ofdm_advance(OfdmState& O, int first, int n, int n_samples, int block_size, cudaStream_t cs) {
-    if (!O.external_ring) return set_error(DABGPU_ERR_STATE, "no device input attached: use dabgpu_ofdm_process");
-    if (n_samples < 0) return set_error(DABGPU_ERR_INVALID, "negative sample count");
-    return ofdm_run(O, first, n, n_samples, block_size > 0 ? block_size : n_samples, cs);
-}
-
-static int ofdm_get_status(OfdmState& O, int stream, dabgpu_ofdm_status* out, cudaStream_t cs) {
-    CUDA_TRY(cudaStreamSynchronize(cs));
-    OfdmStream st;
-    CUDA_TRY(cudaMemcpy(&st, O.dev.st + stream, sizeof(st), cudaMemcpyDeviceToHost));
-    out->state = st.state;
-    out->total_frames_read = st.frames_read;
-    out->total_frames_desync = st.frames_desync;
-    out->fine_time_offset = st.fine_time_offset;
-    out->signal_l1_average = st.l1_avg;
-    out->freq_coarse_offset = st.coarse;
-    out->freq_fine_offset = st.fine;
-    out->frames_queued = 0;
-    return DABGPU_OK;
-}
-
-static int ofdm_fetch_latest(OfdmState& O, int first, int n, int8_t* frames_host, uint8_t* produced, cudaStream_t cs) {
-    int rc;
-    const size_t fb = size_t(O.P.nb_frame_bits);
-    if ((rc = O.d_stage.alloc(size_t(n) * fb))) return rc;
-    const dim3 grid(32, n);
-    k_ofdm_gather_latest<<<grid, 256, 0, cs>>>(O.dev, first, O.d_stage.as<int8_t>(), O.d_produced.as<uint8_t>());
-    O.launches++;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(frames_host, O.d_stage.p, size_t(n) * fb, cudaMemcpyDeviceToHost, cs));
-    CUDA_TRY(cudaMemcpyAsync(O.h_produced.p, O.d_produced.p, size_t(n), cudaMemcpyDeviceToHost, cs));
-    CUDA_TRY(cudaStreamSynchronize(cs));
-    memcpy(produced, O.h_produced.p, size_t(n));
-    return DABGPU_OK;
-}

@@ -143,3 +143,70 @@ def test_ofdm_reset_and_noise_only(gpu_ctx, tx):
     st1 = g.ofdm_status(1)
     assert st1["state"] == 0 and st1["freq_coarse_offset"] == 0.0
     g.close()
+
+
+def test_pipelined_submit_wait_equals_synchronous_process(gpu_ctx, tx, pyref):
+    """dabgpu_submit/dabgpu_wait (copy-in, compute and copy-out overlapped, two tickets in flight) returns exactly the
+    frames and decoded bytes of the synchronous Process() path on the same recordings."""
+    torch = pytest.importorskip("torch")
+    mode, block = 1, 65536
+    subs = [tx.Subchannel(0, 0, 48, eep_level=2), tx.Subchannel(1, 48, 54, eep_level=2, eep_type_b=True, dabplus=False)]
+    n_frames, S = 7, 3
+    recs = [_recording(tx, mode, n_frames, 15.0 + s, (1.1 - s) * 1e-3, 321 + 4000 * s, seed=90 + s, subs=subs)[0] for s in range(S)]
+    P = gpu_ctx.get_params(mode)
+    step = P.nb_frame_samples
+    n_steps = min(r.size for r in recs) // 2 // step
+    host = torch.empty((S, 2 * step * n_steps), dtype=torch.uint8).pin_memory()
+    for s in range(S):
+        host[s].copy_(torch.from_numpy(recs[s][:2 * step * n_steps].copy()))
+    hn = host.numpy()
+
+    g_sync = gpu_ctx.DabGpu(mode=mode, max_streams=S)
+    g_pipe = gpu_ctx.DabGpu(mode=mode, max_streams=S)
+    for g in (g_sync, g_pipe):
+        for s in range(S):
+            g.msc_configure(s, subs)
+    nb = P.nb_frame_bits
+    outs = [dict(frames=torch.empty((S, nb), dtype=torch.int8).pin_memory(), produced=torch.zeros(S, dtype=torch.uint8).pin_memory(),
+                 msc=torch.zeros((S, P.nb_cifs, gpu_ctx.CIF_OUT_STRIDE), dtype=torch.uint8).pin_memory(),
+                 status=torch.zeros((S, 2), dtype=torch.int32).pin_memory()) for _ in range(gpu_ctx.PIPELINE_DEPTH)]
+    expected = []
+    for i in range(n_steps):
+        view = hn[:, 2 * i * step:2 * (i + 1) * step]
+        g_sync.ofdm_process(view, block_size=block)
+        g_sync.chan_decode()
+        fr, pr = g_sync.ofdm_fetch_latest()
+        msc = [[g_sync.get_msc(s, k) for k in range(len(subs))] for s in range(S)]
+        expected.append((fr, pr, msc, [g_sync.chan_status(s) for s in range(S)]))
+
+    def check(i, o):
+        fr, pr, msc, status = expected[i]
+        assert np.array_equal(o["produced"].numpy(), pr)
+        for s in range(S):
+            assert tuple(o["status"].numpy()[s]) == status[s]
+            if pr[s]:
+                assert np.array_equal(o["frames"].numpy()[s], fr[s])
+            if status[s][0]:
+                for k in range(len(subs)):
+                    off, nbytes = g_pipe.msc_layout(s, k)
+                    out, valid = msc[s][k]
+                    for c in range(P.nb_cifs):
+                        if valid[c]:
+                            assert np.array_equal(o["msc"].numpy()[s, c, off:off + nbytes], out[c])
+
+    tickets = []
+    for i in range(n_steps):
+        o = outs[i % len(outs)]
+        if i >= len(outs):
+            g_pipe.wait(tickets[i - len(outs)])
+            check(i - len(outs), o)
+        view = hn[:, 2 * i * step:2 * (i + 1) * step]
+        tickets.append(g_pipe.submit(view.ctypes.data, hn.strides[0], step, block_size=block, run_chan_decode=True,
+                                     frames_host=o["frames"].data_ptr(), produced_host=o["produced"].data_ptr(),
+                                     msc_host=o["msc"].data_ptr(), chan_status_host=o["status"].data_ptr()))
+    for i in range(max(0, n_steps - len(outs)), n_steps):
+        g_pipe.wait(tickets[i])
+        check(i, outs[i % len(outs)])
+    assert sum(int(e[1].sum()) for e in expected) >= S * (n_frames - 3)
+    g_sync.close()
+    g_pipe.close()
