@@ -161,7 +161,12 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
         cudaMemcpy(ctx->d_prbs.p, w.data(), w.size() * 4, cudaMemcpyHostToDevice);
     }
     TRY_OR_FREE(ctx->d_counter.alloc(64));
-    ctx->vit_blocks = ctx->num_sms * 8;
+    // persistent grid: 4 CTAs x 4 warps per SM, each warp with 12.5 KB of decision words in shared memory
+    ctx->vit_blocks = ctx->num_sms * 4;
+    {
+        cudaError_t e = cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, int(VIT_SMEM_BYTES));
+        if (e != cudaSuccess) { rc = set_error(DABGPU_ERR_CUDA, "cudaFuncSetAttribute(k_viterbi): %s", cudaGetErrorString(e)); dabgpu_ctx_destroy(ctx); return rc; }
+    }
     TRY_OR_FREE(ensure_scratch(ctx, 1600));
 
     // frame ring + channel decode buffers
@@ -292,7 +297,7 @@ static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs) 
     CUDA_TRY(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
     const int blocks = ctx->vit_blocks;
     ctx->prof.begin(PROF_VITERBI, ctx->stream);
-    k_viterbi<<<blocks, VIT_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(d_jobs, n_jobs, ctx->d_counter.as<int>(), ctx->d_scratch.as<uint2>(),
+    k_viterbi<<<blocks, VIT_WARPS_PER_BLOCK * 32, VIT_SMEM_BYTES, ctx->stream>>>(d_jobs, n_jobs, ctx->d_counter.as<int>(), ctx->d_scratch.as<uint2>(),
                                                                      ctx->scratch_steps, ctx->d_prbs.as<uint32_t>(), ctx->chan.geom);
     ctx->prof.end(ctx->stream);
     ctx->launches++;

@@ -283,7 +283,7 @@ __device__ __forceinline__ void ctl_l1_batch(const OfdmDev& D, const int s, cons
 }
 
 template <int N>
-__global__ void __launch_bounds__(N / 8)
+__global__ void __launch_bounds__(N / 8, (N == 2048) ? 2 : 4)   // 2048: <= 128 registers so that two CTAs (streams) share an SM
 k_ofdm_ctl(const OfdmDev D, const int first_stream, const int n_new_samples, const int block_size, const int is_first) {
     constexpr int NT = N / 8;
     constexpr int NP = N + N / 8;

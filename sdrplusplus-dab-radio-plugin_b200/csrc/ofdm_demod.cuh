@@ -154,11 +154,16 @@ k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) 
     };
     if (staged && tid == 0) issue_prefetch(l0, 0);
 
-    // per-thread constants: output position of each owned bin (0xFFFF = unused), PLL index terms
-    uint32_t opos[4];
+    // per-thread constants.  The thread owns bins kk + (N/8)*k4: k4 = 1,2,5,6,7 always carry data, k4 = 4 never does, and
+    // exactly one of k4 = 0 (kk != 0) / k4 = 3 (kk == 0: carrier +K/2, while bin 0 is the empty DC carrier) does, so every
+    // thread has six DQPSK products per symbol and the loop below needs no per-bin branch.  op[] = output positions.
+    uint32_t op[6];
+    bool dc_thread;
     {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(D.obin) + tid);
-        opos[0] = v.x; opos[1] = v.y; opos[2] = v.z; opos[3] = v.w;
+        dc_thread = (v.x & 0xFFFFu) == 0xFFFFu;
+        op[0] = dc_thread ? (v.y >> 16) : (v.x & 0xFFFFu);
+        op[1] = v.x >> 16; op[2] = v.y & 0xFFFFu; op[3] = v.z >> 16; op[4] = v.w & 0xFFFFu; op[5] = v.w >> 16;
     }
     float nf[8];
 #pragma unroll
@@ -319,17 +324,16 @@ k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) 
             // DQPSK X_{l-1} * conj(X_l) on the owned bins, L-infinity normalise, truncate to int8
             // (ofdm_demodulator.cpp:842-889: bit0 = trunc(-127*re/A), bit1 = trunc(+127*im/A)).  The scale carries a
             // 1e-6 guard so that the dominant component truncates to exactly +-127 with the approximate reciprocal.
+            const float2 pa[6] = {dc_thread ? prev[3] : prev[0], prev[1], prev[2], prev[5], prev[6], prev[7]};
+            const float2 xb[6] = {dc_thread ? x[3] : x[0], x[1], x[2], x[5], x[6], x[7]};
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint32_t op = (opos[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-                if (op != 0xFFFFu) {
-                    const float2 a = prev[k], b = x[k];
-                    const float vr = a.x * b.x + a.y * b.y;
-                    const float vi = a.y * b.x - a.x * b.y;
-                    const float sc = __fdividef(127.00012f, fmaxf(fabsf(vr), fabsf(vi)));
-                    s_out[op] = uint8_t(int(vr * -sc));
-                    s_out[K + op] = uint8_t(int(vi * sc));
-                }
+            for (int k = 0; k < 6; k++) {
+                const float2 a = pa[k], b = xb[k];
+                const float vr = a.x * b.x + a.y * b.y;
+                const float vi = a.y * b.x - a.x * b.y;
+                const float sc = __fdividef(127.00012f, fmaxf(fabsf(vr), fabsf(vi)));
+                s_out[op[k]] = uint8_t(int(vr * -sc));
+                s_out[K + op[k]] = uint8_t(int(vi * sc));
             }
         }
 #pragma unroll

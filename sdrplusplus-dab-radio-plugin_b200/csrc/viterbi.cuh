@@ -91,6 +91,7 @@ __device__ __forceinline__ uint32_t vit_load_step(const VitJobDev& J, const Gath
     return w;
 }
 
+// ---- exact step (reference arithmetic spelled out: saturating adds, renormalisation check after every step) ----
 #define VIT_ACS_STEP(J_)                                                                            \
     {                                                                                               \
         const uint32_t w_ = __shfl_sync(FULL_MASK, word, (J_));                                     \
@@ -115,82 +116,153 @@ __device__ __forceinline__ uint32_t vit_load_step(const VitJobDev& J, const Gath
         m_lo -= mn_; m_hi -= mn_; acc_err += mn_;                                                   \
     }
 
+// ---- fast step: both metrics of a lane packed as u16x2 and processed by one VIADD / VIMNMX.U16x2 each.
+//   P = (old[l], old[l]), Q = (old[l+32], old[l+32]);  E = (e, 1016-e), E2 = (1016-e, e) built by one IMAD each
+//   A = P + E = (old[l]+e, old[l]+inv), B = Q + E2 = (old[l+32]+inv, old[l+32]+e), NEW = min(A, B) = (new[2l], new[2l+1])
+//   decision = 1 iff the upper predecessor is <= the lower one (tie => 1) iff NEW == B per half.
+// Valid only while no sum can reach 65536 and no renormalisation can trigger, which holds when state 0 stays
+// <= VIT_FAST_SAFE during the chunk (every metric is within 6*1020 of state 0's: any state is reachable from any
+// other in 6 steps) and no soft symbol is -128 (then 1016-e never needs the reference's clamp at 0).  The chunk
+// is verified after the fact and redone with the exact step otherwise.
+#define VIT_FAST_SAFE 58000u
+#define VIT_FAST_STEP(J_)                                                                           \
+    {                                                                                               \
+        const uint32_t w_ = __shfl_sync(FULL_MASK, word, (J_));                                     \
+        uint32_t e_;                                                                                \
+        asm("vabsdiff4.u32.s32.s32.add %0, %1, %2, %3;" : "=r"(e_) : "r"(bt), "r"(w_), "r"(0u));    \
+        const uint32_t E_ = e_ * 0xFFFF0001u + (uint32_t(VIT_MAX_ERROR) << 16);                     \
+        const uint32_t E2_ = e_ * 0x0000FFFFu + uint32_t(VIT_MAX_ERROR);                            \
+        const uint32_t A_ = P + E_, B_ = Q + E2_;                                                   \
+        const uint32_t NEW_ = __vminu2(A_, B_);                                                     \
+        const uint32_t x_ = NEW_ ^ B_;                                                              \
+        const uint32_t be_ = __ballot_sync(FULL_MASK, (x_ & 0xFFFFu) == 0u);                        \
+        const uint32_t bo_ = __ballot_sync(FULL_MASK, (x_ & 0xFFFF0000u) == 0u);                    \
+        if (SM) { if (lane == 0) dec[t0 + (J_)] = make_uint2(be_, bo_); }                           \
+        else if (lane == (J_)) { dec_e = be_; dec_o = bo_; }                                        \
+        const uint32_t a_ = __shfl_sync(FULL_MASK, NEW_, src_lo);                                   \
+        const uint32_t b_ = __shfl_sync(FULL_MASK, NEW_, src_hi);                                   \
+        P = __byte_perm(a_, 0u, dup);                                                               \
+        Q = __byte_perm(b_, 0u, dup);                                                               \
+        mx = max(mx, P);                                                                            \
+    }
+
 __device__ __forceinline__ uint16_t crc16_ccitt_dev(const uint8_t* p, int n) {
     uint32_t crc = 0xFFFFu;
     for (int i = 0; i < n; i++) crc = ((crc << 8) ^ c_crc_ccitt[((crc >> 8) ^ p[i]) & 0xFFu]) & 0xFFFFu;
     return uint16_t(crc ^ 0xFFFFu);
 }
 
-__device__ void vit_decode_job(const VitJobDev& J, const GatherGeom& G, uint2* __restrict__ scratch,
+// Traceback of the bits [b_lo, b_hi] (walking down) from `state`; decoded bit j comes from decision word j+6
+// (viterbi_decoder_core.h:214-236).  When emit is set, completed 32-bit words (big endian: bit 32k is the MSB of
+// word k) are descrambled and stored.  Returns the state reached below b_lo.
+__device__ __forceinline__ uint32_t vit_walk(const uint2* __restrict__ dec, const int b_hi, const int b_lo, uint32_t state, const bool emit,
+                                             const VitJobDev& J, const uint32_t* __restrict__ prbs_words) {
+    uint32_t acc = 0;
+    for (int b = b_hi; b >= b_lo; --b) {
+        const uint32_t* d = reinterpret_cast<const uint32_t*>(dec + (b + 6));
+        const uint32_t w = d[state & 1u];
+        const uint32_t bit = (w >> (state >> 1)) & 1u;
+        state = (state >> 1) | (bit << 5);
+        acc = (acc >> 1) | (bit << 31);
+        if (emit && (b & 31) == 0) {
+            const uint32_t widx = uint32_t(b) >> 5;
+            uint32_t v = acc;
+            if (J.flags & VJ_DESCRAMBLE) v ^= prbs_words[widx];
+            const uint32_t b0 = widx * 4u;
+            if (b0 + 4u <= J.n_out_bytes && ((reinterpret_cast<uintptr_t>(J.out) & 3u) == 0)) {
+                *reinterpret_cast<uint32_t*>(J.out + b0) = __byte_perm(v, 0u, 0x0123);
+            } else {
+#pragma unroll
+                for (uint32_t q = 0; q < 4; q++)
+                    if (b0 + q < J.n_out_bytes) J.out[b0 + q] = uint8_t(v >> (24u - 8u * q));
+            }
+            acc = 0;
+        }
+    }
+    return state;
+}
+
+#define VIT_OVERLAP 128   // speculative traceback: steps walked before a chunk to let the survivors merge
+
+// SM: the decision words of this trellis live in shared memory (written by lane 0 every step); otherwise in the
+// per-warp-slot global scratch (recorded through the lane == step select and stored coalesced per chunk).
+template <bool SM>
+__device__ void vit_decode_job(const VitJobDev& J, const GatherGeom& G, uint2* __restrict__ dec,
                                const uint32_t* __restrict__ prbs_words, const uint32_t lane) {
     const uint32_t N = J.total_steps;
     const uint32_t bt = c_branch[lane];
     const uint32_t src_lo = lane >> 1, src_hi = 16u + (lane >> 1);
-    const uint32_t sel = (lane & 1u) ? 0x4432u : 0x4410u;
+    const uint32_t sel = (lane & 1u) ? 0x4432u : 0x4410u;   // one half, zero extended (exact step)
+    const uint32_t dup = (lane & 1u) ? 0x3232u : 0x1010u;   // one half, duplicated (fast step)
     // ViterbiDecoder_Core::reset (viterbi_decoder_core.h:202-211), config dab_viterbi_decoder.cpp:31-41
-    uint32_t m_lo = (lane == 0) ? 0u : VIT_NONSTART;
-    uint32_t m_hi = VIT_NONSTART;
+    uint32_t P = ((lane == 0) ? 0u : VIT_NONSTART) * 0x10001u;
+    uint32_t Q = VIT_NONSTART * 0x10001u;
     unsigned long long acc_err = 0;
 
+    uint32_t word = (lane < N) ? vit_load_step(J, G, lane) : 0u;
     for (uint32_t t0 = 0; t0 < N; t0 += 32) {
         const uint32_t t = t0 + lane;
-        const uint32_t word = (t < N) ? vit_load_step(J, G, t) : 0u;
+        // prefetch the symbols of the next chunk: the gather goes through L2/HBM and must not sit on the ACS chain
+        const uint32_t next_word = (t + 32u < N) ? vit_load_step(J, G, t + 32u) : 0u;
         uint32_t dec_e = 0, dec_o = 0;
-        const uint32_t m0 = __shfl_sync(FULL_MASK, m_lo, 0);
         const uint32_t n = min(32u, N - t0);
-        if (n == 32u && m0 < VIT_CHUNK_SAFE) {
+        // a -128 symbol makes 1016 - e negative for some branch: needs the clamp of the exact step
+        const uint32_t z = word ^ 0x80808080u;
+        const bool has_m128 = __ballot_sync(FULL_MASK, ((z - 0x01010101u) & ~z & 0x80808080u) != 0u) != 0u;
+        bool done = false;
+        if (n == 32u && !has_m128) {
+            const uint32_t P0 = P, Q0 = Q;
+            uint32_t mx = P;
 #pragma unroll
-            for (int j = 0; j < 32; j++) VIT_ACS_STEP(j)
-        } else {
+            for (int j = 0; j < 32; j++) VIT_FAST_STEP(j)
+            if ((__shfl_sync(FULL_MASK, mx, 0) & 0xFFFFu) <= VIT_FAST_SAFE) done = true;
+            else { P = P0; Q = Q0; }
+        }
+        if (!done) {
+            uint32_t m_lo = P & 0xFFFFu, m_hi = Q & 0xFFFFu;
             for (uint32_t j = 0; j < n; j++) {
                 VIT_ACS_STEP(j)
                 VIT_RENORM_CHECK()
             }
+            P = m_lo * 0x10001u; Q = m_hi * 0x10001u;
+            if (t < N) dec[t] = make_uint2(dec_e, dec_o);
+        } else if (!SM) {
+            dec[t] = make_uint2(dec_e, dec_o);
         }
-        if (t < N) scratch[t] = make_uint2(dec_e, dec_o);
+        word = next_word;
     }
-    if (J.path_error != nullptr && lane == 0) *J.path_error = acc_err + m_lo;
+    if (J.path_error != nullptr && lane == 0) *J.path_error = acc_err + (P & 0xFFFFu);
     __syncwarp();
 
-    // Traceback (viterbi_decoder_core.h:214-236): decoded bit j = decision[j+6][state], state walks
-    // back from 0; bytes are MSB first.  Words are assembled big-endian: bit 31 of word k = bit 32k.
-    const uint32_t nbits = J.n_out_bytes * 8u;
-    const uint32_t nwords = (nbits + 31u) >> 5;
-    uint32_t state = 0, myword = 0;
-    for (int k = int(nwords) - 1; k >= 0; --k) {
-        const uint32_t jlo = uint32_t(k) << 5;
-        const uint32_t m = min(32u, nbits - jlo);
-        uint2 d = make_uint2(0u, 0u);
-        if (lane < m) d = scratch[jlo + lane + 6u];
-        uint32_t acc = 0;
-        if (m == 32u) {
-#pragma unroll
-            for (int i = 31; i >= 0; --i) {
-                const uint32_t w = __shfl_sync(FULL_MASK, (state & 1u) ? d.y : d.x, i);
-                const uint32_t bit = (w >> (state >> 1)) & 1u;
-                state = (state >> 1) | (bit << 5);
-                acc = (acc >> 1) | (bit << 31);
-            }
-        } else {
-            for (int i = int(m) - 1; i >= 0; --i) {
-                const uint32_t w = __shfl_sync(FULL_MASK, (state & 1u) ? d.y : d.x, i);
-                const uint32_t bit = (w >> (state >> 1)) & 1u;
-                state = (state >> 1) | (bit << 5);
-                acc = (acc >> 1) | (bit << 31);
-            }
+    // ---- whole-block traceback from state 0, parallelised over lanes --------------------------------------------
+    // Lane c owns the output words [c*W, (c+1)*W).  Only the top lane knows its start state (0); every other lane
+    // starts VIT_OVERLAP steps above its range from state 0, which puts it on the surviving path with high
+    // probability.  The guess of lane c is then CHECKED against the state the lane above actually reached; any lane
+    // whose guess was wrong is walked again from the verified state (top down), so the result is always the exact
+    // whole-block traceback of the reference.
+    const int nbits = int(J.n_out_bytes) * 8;
+    if (nbits > 0) {
+        const int nwords = (nbits + 31) >> 5;
+        const int W = (nwords + 31) >> 5;
+        const int nact = (nwords + W - 1) / W;
+        const bool active = int(lane) < nact;
+        const int lo_bit = int(lane) * W * 32;
+        const int hi_bit = min((int(lane) + 1) * W * 32, nbits);   // exclusive
+        const bool top = active && (hi_bit == nbits);
+        uint32_t g = 0, h = 0;
+        if (active) {
+            if (!top) g = vit_walk(dec, min(hi_bit + VIT_OVERLAP, nbits) - 1, hi_bit, 0u, false, J, prbs_words);
+            h = vit_walk(dec, hi_bit - 1, lo_bit, g, true, J, prbs_words);
         }
-        if (lane == (uint32_t(k) & 31u)) myword = acc;
-        if ((k & 31) == 0) {
-            const uint32_t widx = uint32_t(k) + lane;
-            if (widx < nwords) {
-                uint32_t v = myword;
-                if (J.flags & VJ_DESCRAMBLE) v ^= prbs_words[widx];
-                const uint32_t b0 = widx * 4u;
-#pragma unroll
-                for (uint32_t b = 0; b < 4; b++)
-                    if (b0 + b < J.n_out_bytes) J.out[b0 + b] = uint8_t(v >> (24u - 8u * b));
+        for (;;) {
+            const uint32_t h_above = __shfl_down_sync(FULL_MASK, h, 1);
+            const uint32_t bad = __ballot_sync(FULL_MASK, active && !top && g != h_above);
+            if (bad == 0u) break;
+            const uint32_t fix = 31u - uint32_t(__clz(int(bad)));   // highest wrong lane: everything above it is verified
+            if (lane == fix) {
+                g = h_above;
+                h = vit_walk(dec, hi_bit - 1, lo_bit, g, true, J, prbs_words);
             }
-            myword = 0;
         }
     }
     if (J.flags & VJ_FIB_CRC) {
@@ -205,14 +277,18 @@ __device__ void vit_decode_job(const VitJobDev& J, const GatherGeom& G, uint2* _
 }
 
 #define VIT_WARPS_PER_BLOCK 4
+#define VIT_SMEM_STEPS 1600   // trellises up to this many steps keep their decisions in shared memory (12.5 KB per warp)
 
 // Persistent kernel: every warp pulls trellises from a global counter until none are left.
 __global__ void __launch_bounds__(VIT_WARPS_PER_BLOCK * 32)
 k_viterbi(const VitJobDev* __restrict__ jobs, const int n_jobs, int* __restrict__ counter, uint2* __restrict__ scratch,
           const uint32_t scratch_steps, const uint32_t* __restrict__ prbs_words, const GatherGeom G) {
+    extern __shared__ uint2 s_dec[];
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t slot = blockIdx.x * VIT_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const uint32_t wib = threadIdx.x >> 5;
+    const uint32_t slot = blockIdx.x * VIT_WARPS_PER_BLOCK + wib;
     uint2* my_scratch = scratch + size_t(slot) * scratch_steps;
+    uint2* my_smem = s_dec + size_t(wib) * VIT_SMEM_STEPS;
     for (;;) {
         int job = 0;
         if (lane == 0) job = atomicAdd(counter, 1);
@@ -220,7 +296,9 @@ k_viterbi(const VitJobDev* __restrict__ jobs, const int n_jobs, int* __restrict_
         if (job >= n_jobs) break;
         const VitJobDev J = jobs[job];
         if (J.total_steps == 0) continue;
-        vit_decode_job(J, G, my_scratch, prbs_words, lane);
+        if (J.total_steps <= VIT_SMEM_STEPS) vit_decode_job<true>(J, G, my_smem, prbs_words, lane);
+        else vit_decode_job<false>(J, G, my_scratch, prbs_words, lane);
         __syncwarp();
     }
 }
+#define VIT_SMEM_BYTES (size_t(VIT_WARPS_PER_BLOCK) * VIT_SMEM_STEPS * sizeof(uint2))
