@@ -66,7 +66,9 @@ typedef struct {
     int max_subchannels;   /* sub-channel table size per stream; 0 = 64 */
     void* cuda_stream;     /* optional cudaStream_t owned by the caller; NULL = library creates one */
     dabgpu_ofdm_config ofdm;
+    unsigned flags;        /* DABGPU_FLAG_* */
 } dabgpu_config;
+#define DABGPU_FLAG_NO_FIC 1u   /* dabgpu_chan_decode skips the FIC (contexts that only serve MSC_Decoder::DecodeCIF) */
 
 DABGPU_API const char* dabgpu_version(void);
 DABGPU_API const char* dabgpu_last_error(void);
@@ -111,6 +113,10 @@ typedef struct {
     float freq_fine_offset;
     int frames_queued;         /* soft-bit frames produced and not yet popped */
 } dabgpu_ofdm_status;
+
+/* OFDM_Demod::GetConfig() is mutable in the reference (the GUI edits it while running, ofdm_demodulator.h:122):
+ * replaces the synchronisation knobs of every stream of the context from the next process/advance call on. */
+DABGPU_API int dabgpu_ofdm_set_config(dabgpu_ctx* ctx, const dabgpu_ofdm_config* cfg);
 
 /* OFDM_Demod::Reset() for one stream (-1 = all streams) */
 DABGPU_API int dabgpu_ofdm_reset(dabgpu_ctx* ctx, int stream);
@@ -199,6 +205,11 @@ DABGPU_API int dabgpu_viterbi_decode(dabgpu_ctx* ctx, const dabgpu_viterbi_job* 
                                      const int8_t* soft_host, size_t soft_bytes,
                                      uint8_t* out_host, size_t out_bytes, uint64_t* path_error_host);
 
+/* FIC_Decoder::DecodeFIBGroup (dab/fic/fic_decoder.cpp:53-117) for n_groups independent FIB groups of 2304 soft
+ * bits each (PI_16 x 21, PI_15 x 3, tail; energy dispersal; CRC16 per FIB).  fibs_host receives n_groups x 3 x 32
+ * descrambled bytes (30 data + 2 CRC), crc_ok one flag per FIB. */
+DABGPU_API int dabgpu_fic_decode(dabgpu_ctx* ctx, const int8_t* soft_host, int n_groups, uint8_t* fibs_host, uint8_t* crc_ok);
+
 /* ---------------------------------------------------------------------------------------------
  * Channel decode of whole transmission frames.
  *   FIC  : replaces BasicFICRunner::Process + FIC_Decoder::DecodeFIBGroup (dab/fic/fic_decoder.cpp:53-117)
@@ -251,6 +262,15 @@ enum { DABGPU_EV_FIRECODE_ERROR = 1, DABGPU_EV_RS_ERROR = 2, DABGPU_EV_SUPERFRAM
 typedef struct { int32_t type, a, b, c, d, n_bytes; } dabgpu_event_header;  /* followed by n_bytes payload padded to 4 */
 DABGPU_API int dabgpu_chan_get_dabplus_events(dabgpu_ctx* ctx, int stream, int sub_index, uint8_t* log_host,
                                               size_t log_cap, size_t* log_bytes);
+
+/* Stand-alone AAC_Frame_Processor (dab/audio/aac_frame_processor.h:37-82): one object per DAB+ sub-channel that is
+ * fed decoded logical frames from the host.  process() consumes one logical frame (MSC_Decoder::DecodeCIF output) and
+ * returns the observer events it fired, in order, in the same flat log format as dabgpu_chan_get_dabplus_events. */
+typedef struct dabgpu_dabplus dabgpu_dabplus;
+DABGPU_API int dabgpu_dabplus_open(dabgpu_ctx* ctx, dabgpu_dabplus** out);
+DABGPU_API void dabgpu_dabplus_close(dabgpu_ctx* ctx, dabgpu_dabplus* p);
+DABGPU_API int dabgpu_dabplus_process(dabgpu_ctx* ctx, dabgpu_dabplus* p, const uint8_t* frame_host, int n_bytes, uint8_t* log_host,
+                                      size_t log_cap, size_t* log_bytes);
 
 /* Reed_Solomon_Decoder::Decode batched (reed_solomon_decoder.h:18-26; GF(2^8)/0x11D, fcr 0, prim 1):
  * n_codewords codewords of (255-pad) bytes each, corrected in place; counts[i] = return value of

@@ -38,7 +38,7 @@ class OfdmConfig(C.Structure):
 class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("transmission_mode", C.c_int), ("max_streams", C.c_int), ("iq_format", C.c_int),
                 ("ring_samples", C.c_size_t), ("frame_slots", C.c_int), ("max_subchannels", C.c_int),
-                ("cuda_stream", C.c_void_p), ("ofdm", OfdmConfig)]
+                ("cuda_stream", C.c_void_p), ("ofdm", OfdmConfig), ("flags", C.c_uint)]
 
 
 class Params(C.Structure):
@@ -99,6 +99,7 @@ EXPORTS = [
     "dabgpu_ofdm_fetch_latest", "dabgpu_viterbi_decode", "dabgpu_msc_configure", "dabgpu_softbits_push", "dabgpu_chan_decode",
     "dabgpu_chan_get_status", "dabgpu_chan_get_fic", "dabgpu_chan_get_msc", "dabgpu_chan_get_dabplus_events", "dabgpu_rs_decode",
     "dabgpu_get_counters", "dabgpu_submit", "dabgpu_wait", "dabgpu_msc_get_layout",
+    "dabgpu_ofdm_set_config", "dabgpu_fic_decode", "dabgpu_dabplus_open", "dabgpu_dabplus_close", "dabgpu_dabplus_process",
 ]
 
 _lib = None
@@ -144,6 +145,12 @@ def load_library() -> C.CDLL:
     L.dabgpu_chan_get_dabplus_events.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.dabgpu_rs_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.dabgpu_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+    L.dabgpu_ofdm_set_config.argtypes = [C.c_void_p, C.POINTER(OfdmConfig)]
+    L.dabgpu_fic_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.dabgpu_dabplus_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.dabgpu_dabplus_close.argtypes = [C.c_void_p, C.c_void_p]
+    L.dabgpu_dabplus_close.restype = None
+    L.dabgpu_dabplus_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.dabgpu_submit.argtypes = [C.c_void_p, C.POINTER(Step), C.POINTER(C.c_uint64)]
     L.dabgpu_wait.argtypes = [C.c_void_p, C.c_uint64]
     L.dabgpu_msc_get_layout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -170,7 +177,8 @@ class DabGpu:
     """One context = one GPU, `max_streams` independent IQ streams (mirrors Radio_Block x N)."""
 
     def __init__(self, mode: int = 1, max_streams: int = 1, device: int = 0, iq_format: int = IQ_U8, ring_samples: int = 0,
-                 frame_slots: int = 0, max_subchannels: int = 0, cuda_stream: Optional[int] = None, ofdm_overrides: Optional[dict] = None):
+                 frame_slots: int = 0, max_subchannels: int = 0, cuda_stream: Optional[int] = None, ofdm_overrides: Optional[dict] = None,
+                 flags: int = 0):
         self.L = load_library()
         cfg = Config()
         self.L.dabgpu_config_default(C.byref(cfg), mode)
@@ -181,6 +189,8 @@ class DabGpu:
         cfg.frame_slots = frame_slots
         cfg.max_subchannels = max_subchannels
         cfg.cuda_stream = cuda_stream
+        cfg.flags = flags
+        self._ofdm_cfg = dict(ofdm_overrides or {})
         for k, v in (ofdm_overrides or {}).items():
             setattr(cfg.ofdm, k, v)
         self.h = C.c_void_p()
@@ -300,6 +310,37 @@ class DabGpu:
         pos = np.zeros((cw.shape[0], nroots), dtype=np.int32)
         _check(self.L.dabgpu_rs_decode(self.h, _ptr(cw), cw.shape[0], nroots, pad, _ptr(counts), _ptr(pos)))
         return counts, cw, pos
+
+    def fic_decode(self, soft: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """soft: [n_groups, 2304] int8 -> (fibs [n_groups, 3, 32], crc_ok [n_groups, 3])"""
+        soft = np.ascontiguousarray(soft, dtype=np.int8).reshape(-1, 2304)
+        fibs = np.zeros((soft.shape[0], 3, 32), dtype=np.uint8)
+        ok = np.zeros((soft.shape[0], 3), dtype=np.uint8)
+        _check(self.L.dabgpu_fic_decode(self.h, _ptr(soft), soft.shape[0], _ptr(fibs), _ptr(ok)))
+        return fibs, ok
+
+    def dabplus_open(self) -> int:
+        h = C.c_void_p()
+        _check(self.L.dabgpu_dabplus_open(self.h, C.byref(h)))
+        return h.value
+
+    def dabplus_close(self, proc: int) -> None:
+        self.L.dabgpu_dabplus_close(self.h, C.c_void_p(proc))
+
+    def dabplus_process(self, proc: int, frame: np.ndarray) -> bytes:
+        frame = np.ascontiguousarray(frame, dtype=np.uint8)
+        buf = np.zeros(1 << 16, dtype=np.uint8)
+        n = C.c_size_t(0)
+        _check(self.L.dabgpu_dabplus_process(self.h, C.c_void_p(proc), _ptr(frame), frame.size, _ptr(buf), buf.size, C.byref(n)))
+        return buf[:n.value].tobytes()
+
+    def ofdm_set_config(self, **kw) -> None:
+        cfg = Config()
+        self.L.dabgpu_config_default(C.byref(cfg), self.mode)
+        for k, v in {**getattr(self, "_ofdm_cfg", {}), **kw}.items():
+            setattr(cfg.ofdm, k, v)
+        self._ofdm_cfg = {**getattr(self, "_ofdm_cfg", {}), **kw}
+        _check(self.L.dabgpu_ofdm_set_config(self.h, C.byref(cfg.ofdm)))
 
     def counters(self) -> dict:
         c = Counters()

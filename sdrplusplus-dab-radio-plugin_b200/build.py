@@ -43,5 +43,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+ROOT = os.path.dirname(HERE)
+ADAPTER_SRC = os.path.join(ROOT, "tests", "host", "adapter_check.cpp")
+ADAPTER_BIN = os.path.join(ROOT, "tests", "host", "_bin", "adapter_check")
+
+
+def build_adapter_check(force: bool = False) -> str:
+    """g++ build of the C++ adapter test driver (host/dab_adapters.hpp over the C ABI), linked against libdabgpu.so."""
+    deps = [ADAPTER_SRC, os.path.join(HERE, "host", "dab_adapters.hpp"), os.path.join(ROOT, "include", "dabgpu.h")]
+    if not force and os.path.exists(ADAPTER_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(ADAPTER_BIN) for d in deps):
+        return ADAPTER_BIN
+    os.makedirs(os.path.dirname(ADAPTER_BIN), exist_ok=True)
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", ADAPTER_BIN, ADAPTER_SRC,
+           "-L" + CSRC, "-ldabgpu", "-Wl,-rpath," + CSRC, "-lpthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building tests/host/adapter_check")
+    return ADAPTER_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

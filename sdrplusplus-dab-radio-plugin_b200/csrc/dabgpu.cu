@@ -93,6 +93,7 @@ void dabgpu_config_default(dabgpu_config* cfg, int transmission_mode) {
     cfg->ofdm.coarse_freq_slow_beta = 0.1f;
     cfg->ofdm.impulse_peak_threshold_db = 20.0f;
     cfg->ofdm.impulse_peak_distance_probability = 0.15f;
+    cfg->flags = 0;
 }
 
 int dabgpu_get_params(int transmission_mode, dabgpu_params* out) {
@@ -210,7 +211,7 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
     C.nb_fibs_per_cif = uint32_t(P.nb_fibs_per_cif);
     C.fib_group_bits = uint32_t(P.nb_fib_group_bits);
     // FIC_Decoder only decodes 2304-bit FIB groups (fic_decoder.cpp:66-72): mode III is skipped like the reference
-    C.fic_enabled = (P.nb_fib_group_bits == 2304) ? 1u : 0u;
+    C.fic_enabled = (P.nb_fib_group_bits == 2304 && !(cfg->flags & DABGPU_FLAG_NO_FIC)) ? 1u : 0u;
     C.max_subs = uint32_t(ctx->max_subs);
     C.jobs_per_stream = uint32_t(P.nb_cifs) * (1u + uint32_t(ctx->max_subs));
     C.frames = ctx->d_frames.as<int8_t>();
@@ -545,6 +546,97 @@ int dabgpu_rs_decode(dabgpu_ctx* ctx, uint8_t* codewords_host, int n_codewords, 
     return dabplus_rs_decode_batch(ctx->dabplus, codewords_host, n_codewords, nroots, pad, counts_host, positions_host, ctx->stream, &ctx->launches);
 }
 
+int dabgpu_fic_decode(dabgpu_ctx* ctx, const int8_t* soft_host, int n_groups, uint8_t* fibs_host, uint8_t* crc_ok) {
+    if (!ctx || !soft_host || !fibs_host || !crc_ok) return set_error(DABGPU_ERR_INVALID, "null argument");
+    if (n_groups <= 0) return DABGPU_OK;
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc;
+    const size_t n = size_t(n_groups);
+    if ((rc = ctx->d_vsoft.alloc(n * 2304 + 16))) return rc;
+    if ((rc = ctx->d_vout.alloc(n * (FIC_GROUP_BYTES + 4) + 16))) return rc;
+    if ((rc = ctx->d_jobs.alloc(n * sizeof(VitJobDev)))) return rc;
+    std::vector<VitJobDev> hj(n);
+    uint8_t* d_crc = ctx->d_vout.as<uint8_t>() + n * FIC_GROUP_BYTES;
+    for (size_t i = 0; i < n; i++) {
+        VitJobDev& J = hj[i];
+        memset(&J, 0, sizeof(J));
+        // PI_16 x 21 blocks, PI_15 x 3 blocks, tail (fic_decoder.cpp:74-85)
+        J.src = ctx->d_vsoft.as<int8_t>() + i * 2304;
+        J.out = ctx->d_vout.as<uint8_t>() + i * FIC_GROUP_BYTES;
+        J.crc_ok = d_crc + i * 4;
+        J.seg_pi[0] = 16; J.seg_pi[1] = 15; J.seg_pi[2] = 0;
+        J.seg_step_end[0] = 672; J.seg_step_end[1] = 768; J.seg_step_end[2] = 774; J.seg_step_end[3] = 774; J.seg_step_end[4] = 774;
+        J.seg_in_base[0] = 0; J.seg_in_base[1] = 2016; J.seg_in_base[2] = 2292;
+        J.n_seg = 3; J.total_steps = 774; J.n_out_bytes = 96;
+        J.flags = VJ_DESCRAMBLE | VJ_FIB_CRC;
+        J.n_fibs = 3;
+    }
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_vsoft.p, soft_host, n * 2304, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_jobs.p, hj.data(), n * sizeof(VitJobDev), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), n_groups))) return rc;
+    std::vector<uint8_t> tmp(n * (FIC_GROUP_BYTES + 4));
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), ctx->d_vout.p, tmp.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < n; i++) {
+        memcpy(fibs_host + i * 96, tmp.data() + i * FIC_GROUP_BYTES, 96);
+        memcpy(crc_ok + i * 3, tmp.data() + n * FIC_GROUP_BYTES + i * 4, 3);
+    }
+    return DABGPU_OK;
+}
+
+struct dabgpu_dabplus { DabPlusProc* d = nullptr; };
+
+int dabgpu_dabplus_open(dabgpu_ctx* ctx, dabgpu_dabplus** out) {
+    if (!ctx || !out) return set_error(DABGPU_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    dabgpu_dabplus* p = new dabgpu_dabplus();
+    cudaError_t e = cudaMalloc(&p->d, sizeof(DabPlusProc));
+    if (e != cudaSuccess) { delete p; return set_error(DABGPU_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    cudaMemset(p->d, 0, sizeof(DabPlusProc));
+    *out = p;
+    return DABGPU_OK;
+}
+
+void dabgpu_dabplus_close(dabgpu_ctx* ctx, dabgpu_dabplus* p) {
+    if (!p) return;
+    if (ctx) { cudaSetDevice(ctx->cfg.device); cudaStreamSynchronize(ctx->stream); }
+    if (p->d) cudaFree(p->d);
+    delete p;
+}
+
+int dabgpu_dabplus_process(dabgpu_ctx* ctx, dabgpu_dabplus* p, const uint8_t* frame_host, int n_bytes, uint8_t* log_host, size_t log_cap, size_t* log_bytes) {
+    if (!ctx || !p || !frame_host) return set_error(DABGPU_ERR_INVALID, "null argument");
+    if (n_bytes < 0 || n_bytes > int(CIF_OUT_STRIDE)) return set_error(DABGPU_ERR_INVALID, "logical frame of %d bytes out of range", n_bytes);
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(p->d->frame, frame_host, size_t(n_bytes), cudaMemcpyHostToDevice, ctx->stream));
+    k_dabplus_direct<<<1, 32, 0, ctx->stream>>>(p->d, n_bytes, ctx->d_counters.as<unsigned long long>());
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    int32_t n_ev = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n_ev, &p->d->n_events, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (n_ev > DP_MAX_EVENTS) return set_error(DABGPU_ERR_OVERFLOW, "event queue overflow (%d events)", n_ev);
+    DabPlusEvent ev[DP_MAX_EVENTS];
+    if (n_ev > 0) CUDA_TRY(cudaMemcpy(ev, p->d->events, size_t(n_ev) * sizeof(DabPlusEvent), cudaMemcpyDeviceToHost));
+    size_t off = 0;
+    for (int i = 0; i < n_ev; i++) {
+        const size_t padded = (size_t(ev[i].payload_len) + 3u) & ~size_t(3);
+        if (off + 24 + padded > log_cap) return set_error(DABGPU_ERR_OVERFLOW, "event log buffer too small");
+        const int32_t hdr[6] = {ev[i].type, ev[i].a, ev[i].b, ev[i].c, ev[i].d, ev[i].payload_len};
+        if (log_host) memcpy(log_host + off, hdr, 24);
+        off += 24;
+        if (ev[i].payload_len > 0) {
+            if (log_host) {
+                memset(log_host + off, 0, padded);
+                CUDA_TRY(cudaMemcpy(log_host + off, p->d->sf_out + ev[i].payload_off, size_t(ev[i].payload_len), cudaMemcpyDeviceToHost));
+            }
+            off += padded;
+        }
+    }
+    if (log_bytes) *log_bytes = off;
+    return DABGPU_OK;
+}
+
 int dabgpu_get_counters(dabgpu_ctx* ctx, dabgpu_counters* out) {
     if (!ctx || !out) return set_error(DABGPU_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
@@ -567,6 +659,14 @@ int dabgpu_get_counters(dabgpu_ctx* ctx, dabgpu_counters* out) {
 // ---------------------------------------------------------------------------------------------
 // OFDM (implementation in ofdm.cuh)
 // ---------------------------------------------------------------------------------------------
+int dabgpu_ofdm_set_config(dabgpu_ctx* ctx, const dabgpu_ofdm_config* cfg) {
+    if (!ctx || !cfg) return set_error(DABGPU_ERR_INVALID, "null argument");
+    if (cfg->signal_l1_nb_samples < 1 || cfg->signal_l1_nb_decimate < 1) return set_error(DABGPU_ERR_INVALID, "signal_l1 window parameters must be >= 1");
+    ctx->cfg.ofdm = *cfg;
+    ctx->ofdm.dev.cfg = *cfg;   // OfdmDev travels by value with every launch: the next call sees the new knobs
+    return DABGPU_OK;
+}
+
 int dabgpu_ofdm_reset(dabgpu_ctx* ctx, int stream) {
     if (!ctx) return set_error(DABGPU_ERR_INVALID, "null context");
     if (stream < -1 || stream >= ctx->cfg.max_streams) return set_error(DABGPU_ERR_INVALID, "stream %d out of range", stream);

@@ -253,6 +253,39 @@ __device__ void dp_superframe(const DpShared& sh, uint8_t* sf, uint8_t* sf_out, 
     }
 }
 
+// AAC_Frame_Processor::Process for one logical frame of n bytes (aac_frame_processor.cpp:126-177), executed by a full
+// warp; all lanes keep identical copies of st.
+__device__ void dp_process_frame(const DpShared& sh, const uint8_t* __restrict__ buf, const int n, DabPlusSubState& st, uint8_t* sf, uint8_t* sf_out,
+                                 const int sf_base, DabPlusEvent* ev, int32_t* n_ev, unsigned long long* counters, const uint32_t lane) {
+    if (n < 11) return;
+    if (st.prev_nb != n) { st.prev_nb = n; st.curr_frame = 0; st.collect = 0; }
+    if (st.desync >= 10) { st.desync = 0; st.synced = 0; }
+    if (st.synced) st.collect = 1;
+    if (!st.collect) {
+        int ok = 0;
+        if (lane == 0) {
+            const uint16_t rx = uint16_t((uint16_t(buf[0]) << 8) | buf[1]);
+            const uint16_t pred = crc16_tab(sh.crc_fire, buf + 2, 9, 0, 0);
+            ok = (rx == pred);
+            if (!ok) dp_emit(ev, n_ev, DABGPU_EV_FIRECODE_ERROR, st.curr_frame, rx, pred, 0, 0, 0);
+        }
+        ok = __shfl_sync(FULL_MASK, ok, 0);
+        if (!ok) return;
+        st.collect = 1;
+    }
+    for (int i = int(lane); i < n; i += 32) sf[size_t(st.curr_frame) * n + i] = buf[i];
+    __syncwarp();
+    st.curr_frame++;
+    if (st.curr_frame == 5) {
+        // lane 0 owns the mutable copy during the superframe step, then broadcasts
+        dp_superframe(sh, sf, sf_out, sf_base, n, st, ev, n_ev, counters, lane);
+        st.desync = __shfl_sync(FULL_MASK, st.desync, 0);
+        st.synced = __shfl_sync(FULL_MASK, st.synced, 0);
+        st.collect = 0;
+        st.curr_frame = 0;
+    }
+}
+
 #define DP_WARPS 4
 __global__ void __launch_bounds__(DP_WARPS * 32)
 k_dabplus(const ChanDev C, const DabPlusDev D, const int first_stream, const int n_streams) {
@@ -277,37 +310,30 @@ k_dabplus(const ChanDev C, const DabPlusDev D, const int first_stream, const int
     for (uint32_t c = 0; c < nb_cifs; c++) {
         if (!C.msc_valid[(size_t(s) * nb_cifs + c) * C.max_subs + sub]) continue;
         const uint8_t* buf = C.msc_out + (size_t(s) * nb_cifs + c) * CIF_OUT_STRIDE + cfg.out_offset;
-        // AAC_Frame_Processor::Process (aac_frame_processor.cpp:126-177); all lanes keep identical copies of st
-        if (n < 11) continue;
-        if (st.prev_nb != n) { st.prev_nb = n; st.curr_frame = 0; st.collect = 0; }
-        if (st.desync >= 10) { st.desync = 0; st.synced = 0; }
-        if (st.synced) st.collect = 1;
-        if (!st.collect) {
-            int ok = 0;
-            if (lane == 0) {
-                const uint16_t rx = uint16_t((uint16_t(buf[0]) << 8) | buf[1]);
-                const uint16_t pred = crc16_tab(sh.crc_fire, buf + 2, 9, 0, 0);
-                ok = (rx == pred);
-                if (!ok) dp_emit(ev, &n_ev_local, DABGPU_EV_FIRECODE_ERROR, st.curr_frame, rx, pred, 0, 0, 0);
-            }
-            ok = __shfl_sync(FULL_MASK, ok, 0);
-            if (!ok) continue;
-            st.collect = 1;
-        }
-        for (int i = int(lane); i < n; i += 32) sf[size_t(st.curr_frame) * n + i] = buf[i];
-        __syncwarp();
-        st.curr_frame++;
-        if (st.curr_frame == 5) {
-            // lane 0 owns the mutable copy during the superframe step, then broadcasts
-            dp_superframe(sh, sf, D.sf_out + size_t(s) * (5u * CIF_OUT_STRIDE) + 5u * cfg.out_offset, int(5u * cfg.out_offset), n, st, ev,
-                          &n_ev_local, C.counters, lane);
-            st.desync = __shfl_sync(FULL_MASK, st.desync, 0);
-            st.synced = __shfl_sync(FULL_MASK, st.synced, 0);
-            st.collect = 0;
-            st.curr_frame = 0;
-        }
+        dp_process_frame(sh, buf, n, st, sf, D.sf_out + size_t(s) * (5u * CIF_OUT_STRIDE) + 5u * cfg.out_offset, int(5u * cfg.out_offset), ev,
+                         &n_ev_local, C.counters, lane);
     }
     if (lane == 0) { D.st[idx] = st; D.n_events[idx] = n_ev_local; }
+}
+
+// Stand-alone AAC_Frame_Processor objects (the C++ adapter of the same name): one warp, one logical frame per call.
+struct DabPlusProc {
+    DabPlusSubState st;
+    int32_t n_events, pad[3];
+    DabPlusEvent events[DP_MAX_EVENTS];
+    uint8_t sf[5 * CIF_OUT_STRIDE];
+    uint8_t sf_out[5 * CIF_OUT_STRIDE];
+    uint8_t frame[CIF_OUT_STRIDE];
+};
+
+__global__ void __launch_bounds__(32) k_dabplus_direct(DabPlusProc* __restrict__ P, const int n, unsigned long long* __restrict__ counters) {
+    __shared__ DpShared sh;
+    dp_load_shared(sh);
+    const uint32_t lane = threadIdx.x;
+    DabPlusSubState st = P->st;
+    int32_t n_ev = 0;
+    dp_process_frame(sh, P->frame, n, st, P->sf, P->sf_out, 0, P->events, &n_ev, counters, lane);
+    if (lane == 0) { P->st = st; P->n_events = n_ev; }
 }
 
 // Reed_Solomon_Decoder::Decode batched: one thread per codeword, corrected in place.

@@ -94,7 +94,7 @@ template <int FMT> __device__ __forceinline__ float2 demod_raw_to_c32(const uint
 __device__ __forceinline__ float2 cmul_tw(const float2 v, const float2* __restrict__ tw, const int idx) { return cmulf(v, __ldg(tw + idx)); }
 
 template <int N, int FMT>
-__global__ void __launch_bounds__(N / 8, (N == 2048) ? 3 : (N == 1024 ? 6 : 8))
+__global__ void __launch_bounds__(N / 8, (N == 2048) ? 4 : (N == 1024 ? 6 : 8))
 k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) {
     using C = DemodCfg<N, FMT>;
     constexpr int T = C::T, CP = C::CP, TSYM = C::TSYM, K = C::K, BPS = C::BPS;

@@ -261,19 +261,21 @@ static int demod_set_attributes(int N, int fmt) {
 }
 
 // Symbols per CTA.  A chunk of c symbols costs c+1 FFTs (the first spectrum is only the DQPSK reference), so fewer, longer
-// chunks waste less; but the grid should fill the resident CTA slots in whole waves.  Pick the split with the lowest
-// (waves x chunk cost) for n streams.
+// chunks waste less; but every SM should end up with the same number of CTAs.  Model fitted to a sweep on B200 (256
+// streams, 4 resident CTAs per SM: 19 symbols per chunk was fastest, then 15, 13, 10, 25, 38): the busiest SM runs
+// ceil(ctas / SMs) CTAs of (spc + 1) symbols each, and k co-resident CTAs deliver perf(k) times the throughput of one.
 static int demod_pick_chunk(const OfdmState& O, int n, int ctas_per_sm) {
+    static const double perf[5] = {1.0, 1.0, 1.9, 2.6, 3.0};
     const int rows = O.P.nb_frame_symbols - 1;
-    const long slots = long(O.num_sms) * ctas_per_sm;
     int best_spc = rows;
     double best = 1e30;
     for (int chunks = 1; chunks <= 16; chunks++) {
         const int spc = (rows + chunks - 1) / chunks;
         const int nch = (rows + spc - 1) / spc;
         const long ctas = long(n) * nch;
-        const long waves = (ctas + slots - 1) / slots;
-        const double cost = double(waves) * double(spc + 1);
+        const long per_sm = (ctas + O.num_sms - 1) / O.num_sms;
+        const int k = int(per_sm < ctas_per_sm ? per_sm : ctas_per_sm);
+        const double cost = double(spc + 1) * double(per_sm) / perf[k > 4 ? 4 : k];
         if (cost < best - 1e-9) { best = cost; best_spc = spc; }
     }
     return best_spc;
@@ -283,8 +285,9 @@ template <int N, int FMT>
 static int ofdm_run_t(OfdmState& O, int first, int n, int n_samples, int block_size, cudaStream_t cs) {
     // a frame consumes at least frame_samples - CP new samples (fine time offset >= -CP), so at most this many complete
     const int max_frames = n_samples / (O.P.nb_frame_samples - O.P.nb_cyclic_prefix) + 1;
-    const int ctas_per_sm = (N == 2048) ? 3 : (N == 1024 ? 6 : 8);
-    const int spc = demod_pick_chunk(O, n, ctas_per_sm);
+    const int ctas_per_sm = (N == 2048) ? 4 : (N == 1024 ? 6 : 8);
+    int spc = demod_pick_chunk(O, n, ctas_per_sm);
+    if (const char* e = getenv("DABGPU_DEMOD_SPC")) { const int v = atoi(e); if (v >= 1 && v < O.P.nb_frame_symbols) spc = v; }   // tuning knob
     const int n_chunks = (O.P.nb_frame_symbols - 1 + spc - 1) / spc;
     const dim3 dgrid(n_chunks, n);
     Profiler& pf = *O.prof;

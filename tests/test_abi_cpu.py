@@ -85,3 +85,25 @@ def test_stream_sharding_two_ranks_gloo():
         assert owned == [1] * n_streams          # every stream owned exactly once
         assert mx == 513
     assert sorted(r[3] for r in res) == [512, 513]
+
+
+def test_cpp_adapters_build_and_fail_loudly_without_gpu(dab):
+    """host/dab_adapters.hpp (the reference's class surfaces over the C ABI) compiles with g++ -std=c++17 and links against
+    libdabgpu.so; without a CUDA device the adapter constructors throw instead of computing anything on the CPU."""
+    import importlib
+    import subprocess
+    import tempfile
+    b = importlib.import_module("sdrplusplus-dab-radio-plugin_b200.build")
+    b.build()
+    exe = b.build_adapter_check()
+    assert os.path.exists(exe)
+    hdr = open(os.path.join(ROOT, "sdrplusplus-dab-radio-plugin_b200", "host", "dab_adapters.hpp")).read()
+    for cls in ("class OFDM_Demod", "class DAB_Viterbi_Decoder", "class FIC_Decoder", "class MSC_Decoder", "class Reed_Solomon_Decoder",
+                "class AAC_Frame_Processor", "class BasicRadio", "class Radio_Block"):
+        assert cls in hdr
+    if dab.load_library().dabgpu_device_count() == 0:
+        with tempfile.TemporaryDirectory() as d:
+            fin = os.path.join(d, "in.bin")
+            open(fin, "wb").write(b"\x00" * 64)
+            res = subprocess.run([exe, "rs", fin, os.path.join(d, "out.bin")], capture_output=True, text=True, timeout=60)
+            assert res.returncode == 3 and "no CPU fallback" in res.stderr
