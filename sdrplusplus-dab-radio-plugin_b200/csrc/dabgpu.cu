@@ -204,6 +204,7 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
 
     ChanDev& C = ctx->chan;
     C.geom.nb_cifs = uint32_t(P.nb_cifs);
+    C.geom.cif_shift = (P.nb_cifs == 4) ? 2u : (P.nb_cifs == 2 ? 1u : 0u);
     C.geom.frame_bits = uint32_t(P.nb_frame_bits);
     C.geom.fic_bits = uint32_t(P.nb_fic_bits);
     C.geom.cif_bits = uint32_t(P.nb_cif_bits);

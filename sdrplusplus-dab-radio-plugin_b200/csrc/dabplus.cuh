@@ -112,11 +112,14 @@ __device__ int rs_solve(const GfTables& T, const uint8_t* S, int nroots, int pad
     return count;
 }
 
+#define DP_WARPS 4
+#define DP_SF_SMEM 1920   // superframes up to 128 kbit/s (5 x 384 bytes) are staged in shared memory per warp
 struct DpShared {
     uint8_t gf_ex[512];
     uint8_t gf_lg[256];
     uint16_t crc_ccitt[256];
     uint16_t crc_fire[256];
+    __align__(16) uint8_t sfbuf[DP_WARPS][DP_SF_SMEM];
 };
 
 __device__ __forceinline__ void dp_load_shared(DpShared& sh) {
@@ -156,23 +159,56 @@ __device__ int dp_read_au_start(const uint8_t* buf, uint16_t* data, int n) {
 }
 
 // ProcessSuperFrame for one sub-channel, executed by a full warp.  Returns nothing; state/event side effects.
-__device__ void dp_superframe(const DpShared& sh, uint8_t* sf, uint8_t* sf_out, const int sf_base, const int nb, DabPlusSubState& st,
+__device__ void dp_superframe(DpShared& sh, uint8_t* sf_global, uint8_t* sf_out, const int sf_base, const int nb, DabPlusSubState& st,
                               DabPlusEvent* ev, int32_t* n_ev, unsigned long long* counters, const uint32_t lane) {
     const GfTables T{sh.gf_ex, sh.gf_lg};
     const int total = nb * 5;
     const int N = total / 120;
-    // ReedSolomonDecode (aac_frame_processor.cpp:322-362)
-    for (int base = 0; base < N; base += 32) {
-        const int i = base + int(lane);
+    // stage the superframe in shared memory: syndromes and CRCs walk it byte by byte (a dependent global load per byte otherwise)
+    uint8_t* sf = sf_global;
+    if (total <= DP_SF_SMEM && (total & 3) == 0 && (reinterpret_cast<uintptr_t>(sf_global) & 3u) == 0) {
+        sf = sh.sfbuf[(threadIdx.x >> 5) % DP_WARPS];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(sf_global);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(sf);
+        for (int i = int(lane); i < total / 4; i += 32) dst[i] = src[i];
+        __syncwarp();
+    }
+    // ReedSolomonDecode (aac_frame_processor.cpp:322-362): codeword i = bytes {i + j*N}.  Eight codewords per pass, four
+    // lanes per codeword: lane part p evaluates the syndromes of roots p, p+4, p+8, the leader lane (p = 0) collects them.
+    for (int base = 0; base < N; base += 8) {
+        const int i = base + int(lane >> 2);
+        const int part = int(lane & 3u);
+        uint8_t Sp[3] = {0, 0, 0};
+        if (i < N) {
+            Sp[0] = Sp[1] = Sp[2] = sf[i];
+            for (int j = 1; j < 120; j++) {
+                const uint8_t d = sf[i + j * N];
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const int r = part + 4 * q;   // root index; r >= 10 is computed but ignored
+                    Sp[q] = uint8_t(d ^ (Sp[q] ? T.ex[gf_mod255(T.lg[Sp[q]] + r)] : 0));
+                }
+            }
+        }
+        uint8_t S[10];
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            const uint32_t packed = uint32_t(Sp[0]) | (uint32_t(Sp[1]) << 8) | (uint32_t(Sp[2]) << 16);
+            const uint32_t v = __shfl_sync(FULL_MASK, packed, (lane & ~3u) + uint32_t(r & 3));
+            S[r] = uint8_t(v >> (8 * (r >> 2)));
+        }
         int cnt = 0;
         uint8_t loc[10], xv[10], ap[10];
-        if (i < N) {
-            uint8_t S[10];
-            if (rs_syndromes(T, sf + i, N, 120, 10, S)) cnt = rs_solve(T, S, 10, 135, loc, xv, ap);
+        const bool leader = (part == 0) && (i < N);
+        if (leader) {
+            int any = 0;
+#pragma unroll
+            for (int r = 0; r < 10; r++) any |= S[r];
+            if (any) cnt = rs_solve(T, S, 10, 135, loc, xv, ap);
         }
-        const uint32_t fail_mask = __ballot_sync(FULL_MASK, cnt < 0);
-        const int first_fail = fail_mask ? (__ffs(int(fail_mask)) - 1) : 32;
-        if (i < N && int(lane) < first_fail) {
+        const uint32_t fail_mask = __ballot_sync(FULL_MASK, leader && cnt < 0);
+        const int first_fail = fail_mask ? ((__ffs(int(fail_mask)) - 1) >> 2) : 8;   // codeword slot inside this pass
+        if (leader && int(lane >> 2) < first_fail) {
             for (int j = 0; j < cnt; j++) {
                 const int k = int(loc[j]) - 135;
                 if (k >= 0 && ap[j]) sf[i + k * N] ^= xv[j];
@@ -255,7 +291,7 @@ __device__ void dp_superframe(const DpShared& sh, uint8_t* sf, uint8_t* sf_out, 
 
 // AAC_Frame_Processor::Process for one logical frame of n bytes (aac_frame_processor.cpp:126-177), executed by a full
 // warp; all lanes keep identical copies of st.
-__device__ void dp_process_frame(const DpShared& sh, const uint8_t* __restrict__ buf, const int n, DabPlusSubState& st, uint8_t* sf, uint8_t* sf_out,
+__device__ void dp_process_frame(DpShared& sh, const uint8_t* __restrict__ buf, const int n, DabPlusSubState& st, uint8_t* sf, uint8_t* sf_out,
                                  const int sf_base, DabPlusEvent* ev, int32_t* n_ev, unsigned long long* counters, const uint32_t lane) {
     if (n < 11) return;
     if (st.prev_nb != n) { st.prev_nb = n; st.curr_frame = 0; st.collect = 0; }
@@ -286,7 +322,6 @@ __device__ void dp_process_frame(const DpShared& sh, const uint8_t* __restrict__
     }
 }
 
-#define DP_WARPS 4
 __global__ void __launch_bounds__(DP_WARPS * 32)
 k_dabplus(const ChanDev C, const DabPlusDev D, const int first_stream, const int n_streams) {
     __shared__ DpShared sh;

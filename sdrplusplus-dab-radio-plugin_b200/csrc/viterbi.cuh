@@ -44,6 +44,7 @@ struct __align__(16) VitJobDev {
 };
 
 struct GatherGeom {
+    uint32_t cif_shift;      // log2(CIFs per transmission frame): 2, 0, 0, 1 for modes I..IV
     uint32_t nb_cifs;        // CIFs per transmission frame
     uint32_t frame_bits;     // soft bits per frame
     uint32_t fic_bits;
@@ -60,10 +61,12 @@ struct GatherGeom {
 
 __device__ __forceinline__ int8_t vit_load_soft(const VitJobDev& J, const GatherGeom& G, uint32_t idx) {
     if (J.flags & VJ_GATHER) {
-        const uint32_t age = c_ti_age[idx & 15u];
+        // bit i of the oldest complete logical frame was sent 15 - T[i mod 16] CIFs before the newest one, and the
+        // interleaver sequence T = {0,8,4,12,...} is the 4-bit reversal of i (cif_deinterleaver.cpp:8-11, 62-68)
+        const uint32_t age = 15u - (__brev(idx) >> 28);
         const uint32_t cabs = J.newest_cif - age;
-        const uint32_t fr = cabs / G.nb_cifs;
-        const uint32_t c = cabs - fr * G.nb_cifs;
+        const uint32_t fr = cabs >> G.cif_shift;
+        const uint32_t c = cabs & (G.nb_cifs - 1u);
         const size_t off = size_t(fr & G.slot_mask) * G.frame_bits + G.fic_bits + size_t(c) * G.cif_bits + J.sub_start_bit + idx;
         return __ldg(J.src + off);
     }
