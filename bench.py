@@ -29,7 +29,9 @@ if ROOT not in sys.path:
 ALG_BYTES_PER_FRAME = 393216 + 230400      # u8 IQ in + int8 soft bits out per Mode I frame
 FRAME_SAMPLES = 196608
 BLOCK = 65536
-NCU_TRAFFIC_PER_FRAME = None               # dram bytes per frame from the committed ncu --set full capture (profiles/), if any
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_ofdm_demod2 launch over 256 frames (ncu --set full, profiles/r1d_ofdm_demod_ncu_full.txt):
+# 99.67 MB + 29.47 MB; below the algorithmic 623616 B/frame because part of the soft-bit rows is still in L2 when the kernel ends
+NCU_TRAFFIC_PER_FRAME = (99666688 + 29469184) / 256
 
 
 def _load_peaks():
@@ -100,21 +102,36 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s), "source": self.source}
 
 
-def cpu_reference_ofdm(n_threads: int, frames_per_thread: int, target_seconds: float):
-    """Times the reference's own OFDM_Demod (oracle/_ref, unmodified sources) or, if that library is absent, the C port,
-    one independent demodulator per thread on `n_threads` host threads.  Returns (MS/s, kind, sample description)."""
+def cpu_reference(n_threads: int, frames_per_thread: int, target_seconds: float, full: bool = False):
+    """Times the reference's own code (oracle/_ref, unmodified sources) or, if that library is absent, the C port, one
+    independent receiver per thread on `n_threads` host threads.  OFDM workload: OFDM_Demod only.  Full workload: OFDM_Demod
+    -> FIC_Decoder + 18 x MSC_Decoder (EEP 3-A) + 18 x AAC_Frame_Processor, i.e. what the GPU does per stream.
+    Returns (MS/s, kind, sample description, wall seconds)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import pyref
     tx = importlib.import_module(PKG + ".synth.dabtx")
     rng = np.random.default_rng(7)
     p = tx.MODES[1]
-    frames = [rng.integers(0, 2, size=p.nb_frame_bits, dtype=np.uint8) for _ in range(frames_per_thread)]
+    subs = tx.default_ensemble()
+    use_chain = full and pyref.ref_available() and hasattr(pyref.RefLib.get().L, "ref_time_chain_u8")
+    if use_chain:
+        ens = tx.EnsembleTx(1, subs, seed=11)
+        frames = [ens.next_frame_bits() for _ in range(frames_per_thread)]
+    else:
+        frames = [rng.integers(0, 2, size=p.nb_frame_bits, dtype=np.uint8) for _ in range(frames_per_thread)]
     iq = tx.ofdm_modulate(frames, 1)
     u8 = tx.to_u8(tx.impair(iq, 15.0, 2.1e-3, 4321, seed=3, tail_samples=2000), 30.0)
     n_samples = u8.size // 2
-    import ctypes as C
-    if pyref.ref_available():
+    what = "OFDM_Demod"
+    if use_chain:
+        L, kind = pyref.RefLib.get().L, "reference"
+        sub_arr = np.array([[sc.start_address, sc.length, int(sc.is_uep), sc.uep_index, sc.eep_level, int(sc.eep_type_b), int(sc.dabplus)]
+                            for sc in subs], dtype=np.int32)
+        counts = np.zeros(4, dtype=np.int64)
+        run = lambda rep: L.ref_time_chain_u8(1, u8, n_samples, BLOCK, rep, sub_arr, len(subs), counts)
+        what = f"OFDM_Demod + FIC_Decoder + {len(subs)} x (MSC_Decoder + AAC_Frame_Processor)"
+    elif pyref.ref_available():
         L, kind = pyref.RefLib.get().L, "reference"
         run = lambda rep: L.ref_time_ofdm_u8(1, u8, n_samples, BLOCK, rep, None)
     else:
@@ -134,8 +151,8 @@ def cpu_reference_ofdm(n_threads: int, frames_per_thread: int, target_seconds: f
         t.join()
     dt = time.perf_counter() - t0
     msps = n_threads * repeat * n_samples / dt / 1e6
-    sample = (f"{n_threads} independent Mode I streams x {repeat}x{frames_per_thread} frames u8 IQ through OFDM_Demod "
-              f"(threads=1 as in the plugin, blocks of {BLOCK}), one demodulator per host thread, {dt:.1f} s wall")
+    sample = (f"{n_threads} independent Mode I streams x {repeat}x{frames_per_thread} frames u8 IQ through {what} "
+              f"(threads=1 as in the plugin, blocks of {BLOCK}), one receiver per host thread, {dt:.1f} s wall")
     return msps, kind, sample, dt
 
 
@@ -146,7 +163,7 @@ def run_reference(args, rank, world):
     vals, total_dt = [], 0.0
     sample = kind = ""
     for i in range(args.warmup + args.steps):
-        msps, kind, sample, dt = cpu_reference_ofdm(cores, 20, 4.0)
+        msps, kind, sample, dt = cpu_reference(cores, 20, 4.0, full=args.workload == "full")
         if i >= args.warmup:
             vals.append(msps)
             total_dt += dt
@@ -155,7 +172,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "dab_mode1_iq_msps", "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_dt / max(len(vals), 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ofdm_demod_mode1_256_streams", "note": "reference CPU OFDM_Demod on all host cores, bounded sample per step"},
+        "config": {"workload": ("full_chain_mode1_" if args.workload == "full" else "ofdm_demod_mode1_") + f"{args.streams}_streams_per_gpu",
+                   "note": "the reference's own CPU code on all host cores, bounded sample per step"},
         "realtime_streams": v / 2.048,
         "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -200,7 +218,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     S, K, W = args.streams, args.steps, args.warmup
-    n_frames = W + K + 2
+    n_frames = W + 2 * K + 2     # K timed steps for `value`, K more with per-kernel CUDA events for the roofline
     full = args.workload == "full"
     payload = None
     subs = tx.default_ensemble()
@@ -235,7 +253,6 @@ def main():
     torch.cuda.synchronize()
     c0 = g.counters()
     launches0 = g.launch_count
-    g.profile_enable(True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     if world > 1:
@@ -248,12 +265,24 @@ def main():
     ev1.record(stream)
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
-    prof = g.profile_read()
-    g.profile_enable(False)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
     c1 = g.counters()
     launches = g.launch_count - launches0
+    # second pass with CUDA events around every kernel launch (dabgpu_profile_*): per-kernel times for the roofline.  The
+    # library serialises its two stream groups while profiling, so this pass is a little slower than the one above.
+    g.profile_enable(True)
+    evp0, evp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evp0.record(stream)
+    for _ in range(K):
+        step()
+    evp1.record(stream)
+    torch.cuda.synchronize()
+    ms_prof = evp0.elapsed_time(evp1)
+    prof = g.profile_read()
+    g.profile_enable(False)
+    c2 = g.counters()
+    frames_prof = c2["frames_demodulated"] - c1["frames_demodulated"]
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
     frames_demod = c1["frames_demodulated"] - c0["frames_demodulated"]
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     fr = torch.tensor([float(frames_demod)], dtype=torch.float64, device=dev)
@@ -331,13 +360,14 @@ def main():
     peak, peak_src = _load_peaks()
     demod_ms = prof["ofdm_demod"]["ms"]
     demod_launches = prof["ofdm_demod"]["launches"]
-    achieved = (frames_demod * ALG_BYTES_PER_FRAME) / (demod_ms * 1e-3) / 1e9 if demod_ms > 0 else 0.0
+    achieved = (frames_prof * ALG_BYTES_PER_FRAME) / (demod_ms * 1e-3) / 1e9 if demod_ms > 0 else 0.0
     roofline = {
         "kernel": "k_ofdm_demod<2048>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": (NCU_TRAFFIC_PER_FRAME * frames_demod / max(demod_launches, 1)) if NCU_TRAFFIC_PER_FRAME else None,
+        "traffic": (NCU_TRAFFIC_PER_FRAME * frames_prof / max(demod_launches, 1)) if NCU_TRAFFIC_PER_FRAME else None,
         "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback 6.65 TB/s (B200_PROFILING.md)",
-        "algorithmic_bytes_per_frame": ALG_BYTES_PER_FRAME, "frames_in_timed_region": frames_demod,
-        "kernel_ms_total": demod_ms, "kernel_launches": demod_launches, "kernel_share_of_step": demod_ms / ms if ms > 0 else None,
+        "algorithmic_bytes_per_frame": ALG_BYTES_PER_FRAME, "frames_in_profiled_pass": frames_prof,
+        "kernel_ms_total": demod_ms, "kernel_launches": demod_launches, "kernel_share_of_step": demod_ms / ms_prof if ms_prof > 0 else None,
+        "profiled_pass_ms_per_step": ms_prof / K,
         "note": "u8 input makes this kernel FP32-issue bound (~100 flop/sample), not HBM bound; see DESIGN.md",
     }
     line = {
@@ -363,7 +393,7 @@ def main():
     g.close()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        v, kind, sample, _ = cpu_reference_ofdm(cores, 20, 12.0)
+        v, kind, sample, _ = cpu_reference(cores, 20, 12.0, full=full)
         line["cpu_baseline"] = {"value": v, "unit": "MS/s", "cores": cores, "kind": kind, "sample": sample}
     if rank == 0:
         print(json.dumps(line))

@@ -98,6 +98,10 @@ class RefLib:
         L.ref_ofdm_get_coarse_response.argtypes = [C.c_void_p, _f32p, C.c_int]
         L.ref_time_ofdm_u8.argtypes = [C.c_int, _u8p, C.c_long, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.ref_time_ofdm_u8.restype = C.c_double
+        if hasattr(L, "ref_time_chain_u8"):
+            L.ref_time_chain_u8.argtypes = [C.c_int, _u8p, C.c_long, C.c_int, C.c_int, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"), C.c_int,
+                                            np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
+            L.ref_time_chain_u8.restype = C.c_double
 
     def build_info(self) -> str:
         return self.L.ref_build_info().decode()

@@ -488,3 +488,68 @@ API double ref_time_ofdm_u8(int mode, const uint8_t* iq, long n_samples, int blo
     ref_ofdm_destroy(r);
     return std::chrono::duration<double>(t1-t0).count();
 }
+
+// Whole receive chain on the CPU, one stream, one thread of control: OFDM_Demod (serial driver, threads=1) -> 4 x
+// FIC_Decoder::DecodeFIBGroup + MSC_Decoder::DecodeCIF per sub-channel and CIF + AAC_Frame_Processor::Process for the
+// DAB+ sub-channels.  subs = n_subs x {start_address, length, is_uep, uep_index, eep_level, eep_type_b, is_dabplus}.
+// counts_out = {frames, fibs_ok, msc_bytes, access_units}.  Returns seconds of wall time.
+API double ref_time_chain_u8(int mode, const uint8_t* iq, long n_samples, int block_size, int repeat, const int* subs, int n_subs,
+                             long long* counts_out) {
+    int dp[13];
+    if (ref_dab_params(mode, dp) != 0) return -1.0;
+    const DAB_Parameters P = get_dab_parameters(mode);
+    auto* r = (RefOfdm*)ref_ofdm_create(mode, 1);
+    if (!r) return -1.0;
+    r->keep_frames = true;
+    void* fic = ref_fic_create(P.nb_fib_cif_bits, P.nb_fibs_per_cif);
+    std::vector<void*> msc, aac;
+    for (int k = 0; k < n_subs; k++) {
+        const int* s = subs + 7*k;
+        msc.push_back(ref_msc_create(s[0], s[1], s[2], s[3], s[4], s[5]));
+        aac.push_back(s[6] ? ref_aac_create() : nullptr);
+    }
+    std::vector<int8_t> frame(static_cast<size_t>(P.nb_frame_bits));
+    std::vector<uint8_t> bytes(8192), log(1 << 16), fibs(30*8);
+    long long frames = 0, fibs_ok = 0, msc_bytes = 0, aus = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int rep = 0; rep < repeat; rep++) {
+        for (long off = 0; off < n_samples; off += block_size) {
+            const long n = (n_samples - off < block_size) ? (n_samples - off) : block_size;
+            ref_ofdm_process_u8(r, iq + 2*off, int(n), 1);
+            float cf[2]; int to;
+            while (ref_ofdm_pop_frame(r, frame.data(), cf, &to) > 0) {
+                frames++;
+                if (P.nb_fib_cif_bits == 2304) {
+                    for (int c = 0; c < P.nb_cifs; c++) fibs_ok += ref_fic_decode_group(fic, frame.data() + c*P.nb_fib_cif_bits, P.nb_fib_cif_bits, c, fibs.data(), 8);
+                }
+                for (int c = 0; c < P.nb_cifs; c++) {
+                    const int8_t* cif = frame.data() + P.nb_fic_bits + c*P.nb_cif_bits;
+                    for (int k = 0; k < n_subs; k++) {
+                        const int nb = ref_msc_decode_cif(msc[size_t(k)], cif, P.nb_cif_bits, bytes.data(), int(bytes.size()));
+                        if (nb > 0) {
+                            msc_bytes += nb;
+                            if (aac[size_t(k)]) {
+                                auto* a = (RefAac*)aac[size_t(k)];
+                                a->log.clear();
+                                a->proc.Process({bytes.data(), size_t(nb)});
+                                for (size_t o = 0; o + 24 <= a->log.size();) {
+                                    int32_t hdr[6];
+                                    memcpy(hdr, &a->log[o], 24);
+                                    if (hdr[0] == EV_AU) aus++;
+                                    o += 24 + ((size_t(hdr[5]) + 3u) & ~size_t(3));
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    if (counts_out) { counts_out[0] = frames; counts_out[1] = fibs_ok; counts_out[2] = msc_bytes; counts_out[3] = aus; }
+    for (auto* m : msc) ref_msc_destroy(m);
+    for (auto* a : aac) if (a) ref_aac_destroy(a);
+    ref_fic_destroy(fic);
+    ref_ofdm_destroy(r);
+    return std::chrono::duration<double>(t1-t0).count();
+}

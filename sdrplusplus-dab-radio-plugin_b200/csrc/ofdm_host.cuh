@@ -18,6 +18,10 @@ struct OfdmState {
     int bps = 2;
     DevBuf d_ring, d_st, d_null_ring, d_corr, d_head, d_phase, d_tw, d_prs_conj, d_prs_time, d_dpos, d_outpos, d_obin, d_stage, d_produced;
     int num_sms = 148;
+    // second stream: the streams of a launch are split in two groups so that the latency-bound control kernel of one
+    // group overlaps the demodulation kernel of the other
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     PinnedBuf h_produced;
     std::vector<unsigned long long> h_written;   // absolute samples written per stream (internal ring)
 };
@@ -222,6 +226,9 @@ static int ofdm_init(OfdmState& O, const dabgpu_config& cfg, const dabgpu_params
         O.num_sms = sms;
     }
     if ((rc = demod_set_attributes(N, cfg.iq_format))) return rc;
+    CUDA_TRY(cudaStreamCreateWithFlags(&O.aux_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&O.ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&O.ev_join, cudaEventDisableTiming));
     D.frames = d_frames;
     D.frames_written = d_frames_written;
     D.frame_info = d_frame_info;
@@ -234,6 +241,10 @@ static void ofdm_destroy(OfdmState& O) {
     DevBuf* bufs[] = {&O.d_ring, &O.d_st, &O.d_null_ring, &O.d_corr, &O.d_head, &O.d_phase, &O.d_tw, &O.d_prs_conj, &O.d_prs_time,
                       &O.d_dpos, &O.d_outpos, &O.d_obin, &O.d_stage, &O.d_produced};
     for (DevBuf* b : bufs) b->release();
+    if (O.aux_stream) { cudaStreamSynchronize(O.aux_stream); cudaStreamDestroy(O.aux_stream); O.aux_stream = nullptr; }
+    if (O.ev_fork) cudaEventDestroy(O.ev_fork);
+    if (O.ev_join) cudaEventDestroy(O.ev_join);
+    O.ev_fork = O.ev_join = nullptr;
     O.h_produced.release();
 }
 
@@ -282,9 +293,7 @@ static int demod_pick_chunk(const OfdmState& O, int n, int ctas_per_sm) {
 }
 
 template <int N, int FMT>
-static int ofdm_run_t(OfdmState& O, int first, int n, int n_samples, int block_size, cudaStream_t cs) {
-    // a frame consumes at least frame_samples - CP new samples (fine time offset >= -CP), so at most this many complete
-    const int max_frames = n_samples / (O.P.nb_frame_samples - O.P.nb_cyclic_prefix) + 1;
+static void ofdm_launch_group(OfdmState& O, int first, int n, int n_samples, int block_size, int max_frames, cudaStream_t cs) {
     const int ctas_per_sm = (N == 2048) ? 4 : (N == 1024 ? 6 : 8);
     int spc = demod_pick_chunk(O, n, ctas_per_sm);
     if (const char* e = getenv("DABGPU_DEMOD_SPC")) { const int v = atoi(e); if (v >= 1 && v < O.P.nb_frame_symbols) spc = v; }   // tuning knob
@@ -304,6 +313,25 @@ static int ofdm_run_t(OfdmState& O, int first, int n, int n_samples, int block_s
     k_ofdm_ctl<N><<<n, N / 8, 0, cs>>>(O.dev, first, n_samples, block_size, 0);
     pf.end(cs);
     O.launches++;
+}
+
+template <int N, int FMT>
+static int ofdm_run_t(OfdmState& O, int first, int n, int n_samples, int block_size, cudaStream_t cs) {
+    // a frame consumes at least frame_samples - CP new samples (fine time offset >= -CP), so at most this many complete
+    const int max_frames = n_samples / (O.P.nb_frame_samples - O.P.nb_cyclic_prefix) + 1;
+    // two groups on two CUDA streams (kernel timing by class is only meaningful without the overlap: off when profiling)
+    const bool split = n >= 64 && !O.prof->on && O.aux_stream != nullptr && getenv("DABGPU_NO_OVERLAP") == nullptr;
+    if (!split) {
+        ofdm_launch_group<N, FMT>(O, first, n, n_samples, block_size, max_frames, cs);
+    } else {
+        const int n0 = n / 2;
+        CUDA_TRY(cudaEventRecord(O.ev_fork, cs));
+        CUDA_TRY(cudaStreamWaitEvent(O.aux_stream, O.ev_fork, 0));
+        ofdm_launch_group<N, FMT>(O, first, n0, n_samples, block_size, max_frames, cs);
+        ofdm_launch_group<N, FMT>(O, first + n0, n - n0, n_samples, block_size, max_frames, O.aux_stream);
+        CUDA_TRY(cudaEventRecord(O.ev_join, O.aux_stream));
+        CUDA_TRY(cudaStreamWaitEvent(cs, O.ev_join, 0));
+    }
     CUDA_TRY(cudaGetLastError());
     return DABGPU_OK;
 }
