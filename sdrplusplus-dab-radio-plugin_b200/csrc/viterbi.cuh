@@ -59,23 +59,27 @@ struct GatherGeom {
 // renormalisation threshold inside the chunk: the per-step check can be skipped without changing results.
 #define VIT_CHUNK_SAFE (VIT_RENORM - 32u * 1020u)
 
-__device__ __forceinline__ int8_t vit_load_soft(const VitJobDev& J, const GatherGeom& G, uint32_t idx) {
-    if (J.flags & VJ_GATHER) {
-        // bit i of the oldest complete logical frame was sent 15 - T[i mod 16] CIFs before the newest one, and the
-        // interleaver sequence T = {0,8,4,12,...} is the 4-bit reversal of i (cif_deinterleaver.cpp:8-11, 62-68)
-        const uint32_t age = 15u - (__brev(idx) >> 28);
-        const uint32_t cabs = J.newest_cif - age;
-        const uint32_t fr = cabs >> G.cif_shift;
-        const uint32_t c = cabs & (G.nb_cifs - 1u);
-        const size_t off = size_t(fr & G.slot_mask) * G.frame_bits + G.fic_bits + size_t(c) * G.cif_bits + J.sub_start_bit + idx;
-        return __ldg(J.src + off);
+// Per-trellis gather table: s_rowoff[r] is the offset (relative to J.src) of the CIF row that holds the soft bits whose
+// index is r modulo 16, so a soft bit is fetched from J.src[s_rowoff[idx & 15] + idx].  Bit i of the oldest complete logical
+// frame was sent 15 - T[i mod 16] CIFs before the newest one, and the interleaver sequence T = {0,8,4,12,...} is the 4-bit
+// reversal of i (cif_deinterleaver.cpp:8-11, 62-68).  Linear jobs (no time de-interleaver) get an all-zero table.
+__device__ __forceinline__ void vit_fill_rowoff(const VitJobDev& J, const GatherGeom& G, uint32_t* s_rowoff, const uint32_t lane) {
+    if (lane < 16u) {
+        uint32_t off = 0;
+        if (J.flags & VJ_GATHER) {
+            const uint32_t age = 15u - (__brev(lane) >> 28);
+            const uint32_t cabs = J.newest_cif - age;
+            const uint32_t fr = cabs >> G.cif_shift;
+            const uint32_t c = cabs & (G.nb_cifs - 1u);
+            off = (fr & G.slot_mask) * G.frame_bits + G.fic_bits + c * G.cif_bits + J.sub_start_bit;
+        }
+        s_rowoff[lane] = off;
     }
-    return __ldg(J.src + idx);
 }
 
 // Depuncture on the fly: mother-code symbols of trellis step t packed as 4 int8 (punctured => 0).
 // Reference: DAB_Viterbi_Decoder::depuncture_symbols, dab_viterbi_decoder.cpp:131-181
-__device__ __forceinline__ uint32_t vit_load_step(const VitJobDev& J, const GatherGeom& G, uint32_t t) {
+__device__ __forceinline__ uint32_t vit_load_step(const VitJobDev& J, const uint32_t* s_rowoff, uint32_t t) {
     uint32_t start = 0, pi = J.seg_pi[0], inb = J.seg_in_base[0];
 #pragma unroll
     for (int i = 0; i < DABGPU_MAX_SEGMENTS - 1; i++) {
@@ -89,15 +93,23 @@ __device__ __forceinline__ uint32_t vit_load_step(const VitJobDev& J, const Gath
     uint32_t w = 0;
 #pragma unroll
     for (uint32_t r = 0; r < 4; r++) {
-        if (r < cnt) w |= uint32_t(uint8_t(vit_load_soft(J, G, base + r))) << (8u * r);
+        if (r < cnt) {
+            const uint32_t idx = base + r;
+            w |= uint32_t(uint8_t(__ldg(J.src + (size_t(s_rowoff[idx & 15u]) + idx)))) << (8u * r);
+        }
     }
     return w;
 }
 
+// The symbols of the 32 steps of a chunk sit in shared memory (one word per step, written by the lane that fetched it)
+// and are read back as warp-uniform 128-bit loads, four steps at a time.
+#define VIT_WORD(J_) ((((J_) & 3) == 0) ? wq.x : (((J_) & 3) == 1) ? wq.y : (((J_) & 3) == 2) ? wq.z : wq.w)
+#define VIT_WORD_FETCH(J_) if (((J_) & 3) == 0) wq = reinterpret_cast<const uint4*>(s_words)[(J_) >> 2];
+
 // ---- exact step (reference arithmetic spelled out: saturating adds, renormalisation check after every step) ----
 #define VIT_ACS_STEP(J_)                                                                            \
     {                                                                                               \
-        const uint32_t w_ = __shfl_sync(FULL_MASK, word, (J_));                                     \
+        const uint32_t w_ = s_words[(J_)];                                                          \
         uint32_t e_;                                                                                \
         asm("vabsdiff4.u32.s32.s32.add %0, %1, %2, %3;" : "=r"(e_) : "r"(bt), "r"(w_), "r"(0u));    \
         const uint32_t inv_ = uint32_t(max(VIT_MAX_ERROR - int(e_), 0));                            \
@@ -121,25 +133,26 @@ __device__ __forceinline__ uint32_t vit_load_step(const VitJobDev& J, const Gath
 
 // ---- fast step: both metrics of a lane packed as u16x2 and processed by one VIADD / VIMNMX.U16x2 each.
 //   P = (old[l], old[l]), Q = (old[l+32], old[l+32]);  E = (e, 1016-e), E2 = (1016-e, e) built by one IMAD each
-//   A = P + E = (old[l]+e, old[l]+inv), B = Q + E2 = (old[l+32]+inv, old[l+32]+e), NEW = min(A, B) = (new[2l], new[2l+1])
-//   decision = 1 iff the upper predecessor is <= the lower one (tie => 1) iff NEW == B per half.
+//   A = P + E = (old[l]+e, old[l]+inv), B = Q + E2 = (old[l+32]+inv, old[l+32]+e), NEW = min(B, A) = (new[2l], new[2l+1])
+//   decision = 1 iff the upper predecessor is <= the lower one (tie => 1): these are the two predicate outputs of
+//   VIMNMX.U16x2 (per-halfword B <= A), so the decisions cost no instruction beyond the two ballots.
 // Valid only while no sum can reach 65536 and no renormalisation can trigger, which holds when state 0 stays
 // <= VIT_FAST_SAFE during the chunk (every metric is within 6*1020 of state 0's: any state is reachable from any
 // other in 6 steps) and no soft symbol is -128 (then 1016-e never needs the reference's clamp at 0).  The chunk
-// is verified after the fact and redone with the exact step otherwise.
+// is verified after the fact and redone with an exact step otherwise.
 #define VIT_FAST_SAFE 58000u
 #define VIT_FAST_STEP(J_)                                                                           \
     {                                                                                               \
-        const uint32_t w_ = __shfl_sync(FULL_MASK, word, (J_));                                     \
+        VIT_WORD_FETCH(J_)                                                                          \
+        const uint32_t w_ = VIT_WORD(J_);                                                           \
         uint32_t e_;                                                                                \
         asm("vabsdiff4.u32.s32.s32.add %0, %1, %2, %3;" : "=r"(e_) : "r"(bt), "r"(w_), "r"(0u));    \
         const uint32_t E_ = e_ * 0xFFFF0001u + (uint32_t(VIT_MAX_ERROR) << 16);                     \
         const uint32_t E2_ = e_ * 0x0000FFFFu + uint32_t(VIT_MAX_ERROR);                            \
-        const uint32_t A_ = P + E_, B_ = Q + E2_;                                                   \
-        const uint32_t NEW_ = __vminu2(A_, B_);                                                     \
-        const uint32_t x_ = NEW_ ^ B_;                                                              \
-        const uint32_t be_ = __ballot_sync(FULL_MASK, (x_ & 0xFFFFu) == 0u);                        \
-        const uint32_t bo_ = __ballot_sync(FULL_MASK, (x_ & 0xFFFF0000u) == 0u);                    \
+        bool ph_, pl_;                                                                              \
+        const uint32_t NEW_ = __vibmin_u16x2(Q + E2_, P + E_, &ph_, &pl_);                          \
+        const uint32_t be_ = __ballot_sync(FULL_MASK, pl_);                                         \
+        const uint32_t bo_ = __ballot_sync(FULL_MASK, ph_);                                         \
         if (SM) { if (lane == 0) dec[t0 + (J_)] = make_uint2(be_, bo_); }                           \
         else if (lane == (J_)) { dec_e = be_; dec_o = bo_; }                                        \
         const uint32_t a_ = __shfl_sync(FULL_MASK, NEW_, src_lo);                                   \
@@ -147,6 +160,37 @@ __device__ __forceinline__ uint32_t vit_load_step(const VitJobDev& J, const Gath
         P = __byte_perm(a_, 0u, dup);                                                               \
         Q = __byte_perm(b_, 0u, dup);                                                               \
         mx = max(mx, P);                                                                            \
+    }
+
+// ---- packed exact step: the same u16x2 arithmetic with the reference's saturation and renormalisation reproduced.
+// Metrics are held with a bias of -VIT_PK_BIAS so that a sum can exceed the saturation level without wrapping the
+// halfword: ref 65535 <-> stored VIT_PK_CLAMP, and min(sum, VIT_PK_CLAMP) per halfword IS the saturating add of the
+// reference.  Needs every metric >= VIT_PK_BIAS at the start of the chunk (guaranteed when state 0 >= VIT_PK_MIN0, by
+// the 6-step reachability bound) and no -128 symbol.  The renormalisation test (state 0 >= 60455 after the step) is made
+// every step; when it fires the metrics are renormalised exactly as the reference does (subtract the minimum) and the
+// rest of the chunk runs on the scalar exact step, because the renormalised metrics fall below the bias.
+#define VIT_PK_BIAS 1024u
+#define VIT_PK_CLAMP ((65535u - VIT_PK_BIAS) * 0x10001u)
+#define VIT_PK_RENORM ((VIT_RENORM - VIT_PK_BIAS) * 0x10001u)
+#define VIT_PK_MIN0 (VIT_PK_BIAS + 6u * 1020u)
+#define VIT_PK_STEP(J_)                                                                             \
+    {                                                                                               \
+        VIT_WORD_FETCH(J_)                                                                          \
+        const uint32_t w_ = VIT_WORD(J_);                                                           \
+        uint32_t e_;                                                                                \
+        asm("vabsdiff4.u32.s32.s32.add %0, %1, %2, %3;" : "=r"(e_) : "r"(bt), "r"(w_), "r"(0u));    \
+        const uint32_t E_ = e_ * 0xFFFF0001u + (uint32_t(VIT_MAX_ERROR) << 16);                     \
+        const uint32_t E2_ = e_ * 0x0000FFFFu + uint32_t(VIT_MAX_ERROR);                            \
+        const uint32_t A_ = __vminu2(P + E_, VIT_PK_CLAMP), B_ = __vminu2(Q + E2_, VIT_PK_CLAMP);   \
+        bool ph_, pl_;                                                                              \
+        const uint32_t NEW_ = __vibmin_u16x2(B_, A_, &ph_, &pl_);                                   \
+        const uint32_t be_ = __ballot_sync(FULL_MASK, pl_);                                         \
+        const uint32_t bo_ = __ballot_sync(FULL_MASK, ph_);                                         \
+        if (lane == (J_)) { dec_e = be_; dec_o = bo_; }                                             \
+        const uint32_t a_ = __shfl_sync(FULL_MASK, NEW_, src_lo);                                   \
+        const uint32_t b_ = __shfl_sync(FULL_MASK, NEW_, src_hi);                                   \
+        P = __byte_perm(a_, 0u, dup);                                                               \
+        Q = __byte_perm(b_, 0u, dup);                                                               \
     }
 
 __device__ __forceinline__ uint16_t crc16_ccitt_dev(const uint8_t* p, int n) {
@@ -189,49 +233,85 @@ __device__ __forceinline__ uint32_t vit_walk(const uint2* __restrict__ dec, cons
 
 // SM: the decision words of this trellis live in shared memory (written by lane 0 every step); otherwise in the
 // per-warp-slot global scratch (recorded through the lane == step select and stored coalesced per chunk).
+// Three step variants, always bit-identical to the reference:
+//   fast   (VIT_FAST_STEP)  : packed, no saturation / renormalisation handling, verified after the chunk
+//   packed (VIT_PK_STEP)    : packed with the reference's saturation and renormalisation, for the chunks around a
+//                             renormalisation (state 0 between VIT_FAST_SAFE and VIT_RENORM)
+//   scalar (VIT_ACS_STEP)   : the reference arithmetic spelled out; partial chunks, -128 symbols, and the steps that
+//                             follow a renormalisation inside a chunk
 template <bool SM>
-__device__ void vit_decode_job(const VitJobDev& J, const GatherGeom& G, uint2* __restrict__ dec,
-                               const uint32_t* __restrict__ prbs_words, const uint32_t lane) {
+__device__ void vit_decode_job(const VitJobDev& J, uint2* __restrict__ dec, uint32_t* __restrict__ s_words,
+                               const uint32_t* __restrict__ s_rowoff, const uint32_t* __restrict__ prbs_words, const uint32_t lane) {
     const uint32_t N = J.total_steps;
     const uint32_t bt = c_branch[lane];
     const uint32_t src_lo = lane >> 1, src_hi = 16u + (lane >> 1);
-    const uint32_t sel = (lane & 1u) ? 0x4432u : 0x4410u;   // one half, zero extended (exact step)
-    const uint32_t dup = (lane & 1u) ? 0x3232u : 0x1010u;   // one half, duplicated (fast step)
+    const uint32_t sel = (lane & 1u) ? 0x4432u : 0x4410u;   // one half, zero extended (scalar step)
+    const uint32_t dup = (lane & 1u) ? 0x3232u : 0x1010u;   // one half, duplicated (packed steps)
     // ViterbiDecoder_Core::reset (viterbi_decoder_core.h:202-211), config dab_viterbi_decoder.cpp:31-41
     uint32_t P = ((lane == 0) ? 0u : VIT_NONSTART) * 0x10001u;
     uint32_t Q = VIT_NONSTART * 0x10001u;
     unsigned long long acc_err = 0;
+    uint32_t growth = 0;   // growth of state 0's metric over the previous chunk: predicts whether the fast step can hold
 
-    uint32_t word = (lane < N) ? vit_load_step(J, G, lane) : 0u;
+    uint32_t word = (lane < N) ? vit_load_step(J, s_rowoff, lane) : 0u;
     for (uint32_t t0 = 0; t0 < N; t0 += 32) {
         const uint32_t t = t0 + lane;
+        __syncwarp();            // every lane is done with the previous chunk's symbols
+        s_words[lane] = word;
+        __syncwarp();
         // prefetch the symbols of the next chunk: the gather goes through L2/HBM and must not sit on the ACS chain
-        const uint32_t next_word = (t + 32u < N) ? vit_load_step(J, G, t + 32u) : 0u;
+        const uint32_t next_word = (t + 32u < N) ? vit_load_step(J, s_rowoff, t + 32u) : 0u;
         uint32_t dec_e = 0, dec_o = 0;
         const uint32_t n = min(32u, N - t0);
-        // a -128 symbol makes 1016 - e negative for some branch: needs the clamp of the exact step
+        // a -128 symbol makes 1016 - e negative for some branch: needs the clamp of the scalar step
         const uint32_t z = word ^ 0x80808080u;
         const bool has_m128 = __ballot_sync(FULL_MASK, ((z - 0x01010101u) & ~z & 0x80808080u) != 0u) != 0u;
-        bool done = false;
+        const uint32_t m0 = __shfl_sync(FULL_MASK, P, 0) & 0xFFFFu;
+        bool done = false, stored = false;
+        uint32_t jr = 0;         // first step left to the scalar loop
+        uint32_t m_lo = 0, m_hi = 0;
+        uint4 wq;
         if (n == 32u && !has_m128) {
-            const uint32_t P0 = P, Q0 = Q;
-            uint32_t mx = P;
+            const bool pk_ok = m0 >= VIT_PK_MIN0;
+            if (!pk_ok || m0 + growth + 256u <= VIT_FAST_SAFE) {
+                const uint32_t P0 = P, Q0 = Q;
+                uint32_t mx = P;
 #pragma unroll
-            for (int j = 0; j < 32; j++) VIT_FAST_STEP(j)
-            if ((__shfl_sync(FULL_MASK, mx, 0) & 0xFFFFu) <= VIT_FAST_SAFE) done = true;
-            else { P = P0; Q = Q0; }
+                for (int j = 0; j < 32; j++) VIT_FAST_STEP(j)
+                if ((__shfl_sync(FULL_MASK, mx, 0) & 0xFFFFu) <= VIT_FAST_SAFE) { done = true; stored = SM; }
+                else { P = P0; Q = Q0; }
+            }
+            if (!done && pk_ok) {
+                P -= VIT_PK_BIAS * 0x10001u; Q -= VIT_PK_BIAS * 0x10001u;
+                jr = 32u;
+                bool fired = false;
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    VIT_PK_STEP(j)
+                    if (__any_sync(FULL_MASK, lane == 0u && P >= VIT_PK_RENORM)) { fired = true; jr = uint32_t(j) + 1u; break; }
+                }
+                if (fired) {
+                    // ViterbiDecoder_AVX_u16::renormalise: subtract the minimum over the 64 states
+                    const uint32_t mn = __reduce_min_sync(FULL_MASK, min(P & 0xFFFFu, Q & 0xFFFFu));
+                    m_lo = (P & 0xFFFFu) - mn; m_hi = (Q & 0xFFFFu) - mn;
+                    acc_err += mn + VIT_PK_BIAS;
+                } else {
+                    P += VIT_PK_BIAS * 0x10001u; Q += VIT_PK_BIAS * 0x10001u;
+                    done = true;
+                }
+            }
         }
         if (!done) {
-            uint32_t m_lo = P & 0xFFFFu, m_hi = Q & 0xFFFFu;
-            for (uint32_t j = 0; j < n; j++) {
+            if (jr == 0u) { m_lo = P & 0xFFFFu; m_hi = Q & 0xFFFFu; }
+            for (uint32_t j = jr; j < n; j++) {
                 VIT_ACS_STEP(j)
                 VIT_RENORM_CHECK()
             }
             P = m_lo * 0x10001u; Q = m_hi * 0x10001u;
-            if (t < N) dec[t] = make_uint2(dec_e, dec_o);
-        } else if (!SM) {
-            dec[t] = make_uint2(dec_e, dec_o);
         }
+        if (!stored && t < N) dec[t] = make_uint2(dec_e, dec_o);
+        const uint32_t m0_end = __shfl_sync(FULL_MASK, P, 0) & 0xFFFFu;
+        growth = (m0_end > m0) ? (m0_end - m0) : 0u;
         word = next_word;
     }
     if (J.path_error != nullptr && lane == 0) *J.path_error = acc_err + (P & 0xFFFFu);
@@ -281,17 +361,21 @@ __device__ void vit_decode_job(const VitJobDev& J, const GatherGeom& G, uint2* _
 
 #define VIT_WARPS_PER_BLOCK 4
 #define VIT_SMEM_STEPS 1600   // trellises up to this many steps keep their decisions in shared memory (12.5 KB per warp)
+#define VIT_WARP_SMEM (size_t(VIT_SMEM_STEPS) * sizeof(uint2) + 32 * 4 + 16 * 4)   // decisions + chunk symbols + gather table
 
 // Persistent kernel: every warp pulls trellises from a global counter until none are left.
 __global__ void __launch_bounds__(VIT_WARPS_PER_BLOCK * 32)
 k_viterbi(const VitJobDev* __restrict__ jobs, const int n_jobs, int* __restrict__ counter, uint2* __restrict__ scratch,
           const uint32_t scratch_steps, const uint32_t* __restrict__ prbs_words, const GatherGeom G) {
-    extern __shared__ uint2 s_dec[];
+    extern __shared__ __align__(16) uint8_t s_vit[];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t wib = threadIdx.x >> 5;
     const uint32_t slot = blockIdx.x * VIT_WARPS_PER_BLOCK + wib;
     uint2* my_scratch = scratch + size_t(slot) * scratch_steps;
-    uint2* my_smem = s_dec + size_t(wib) * VIT_SMEM_STEPS;
+    uint8_t* base = s_vit + size_t(wib) * VIT_WARP_SMEM;
+    uint2* my_smem = reinterpret_cast<uint2*>(base);
+    uint32_t* s_words = reinterpret_cast<uint32_t*>(base + size_t(VIT_SMEM_STEPS) * sizeof(uint2));
+    uint32_t* s_rowoff = s_words + 32;
     for (;;) {
         int job = 0;
         if (lane == 0) job = atomicAdd(counter, 1);
@@ -299,9 +383,12 @@ k_viterbi(const VitJobDev* __restrict__ jobs, const int n_jobs, int* __restrict_
         if (job >= n_jobs) break;
         const VitJobDev J = jobs[job];
         if (J.total_steps == 0) continue;
-        if (J.total_steps <= VIT_SMEM_STEPS) vit_decode_job<true>(J, G, my_smem, prbs_words, lane);
-        else vit_decode_job<false>(J, G, my_scratch, prbs_words, lane);
+        __syncwarp();
+        vit_fill_rowoff(J, G, s_rowoff, lane);
+        __syncwarp();
+        if (J.total_steps <= VIT_SMEM_STEPS) vit_decode_job<true>(J, my_smem, s_words, s_rowoff, prbs_words, lane);
+        else vit_decode_job<false>(J, my_scratch, s_words, s_rowoff, prbs_words, lane);
         __syncwarp();
     }
 }
-#define VIT_SMEM_BYTES (size_t(VIT_WARPS_PER_BLOCK) * VIT_SMEM_STEPS * sizeof(uint2))
+#define VIT_SMEM_BYTES (size_t(VIT_WARPS_PER_BLOCK) * VIT_WARP_SMEM)
