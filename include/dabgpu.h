@@ -69,6 +69,10 @@ typedef struct {
     unsigned flags;        /* DABGPU_FLAG_* */
 } dabgpu_config;
 #define DABGPU_FLAG_NO_FIC 1u   /* dabgpu_chan_decode skips the FIC (contexts that only serve MSC_Decoder::DecodeCIF) */
+/* Viterbi mapping.  Default: calls with thousands of trellises run one trellis per lane (k_viterbi_lanes), smaller calls
+ * one trellis per warp (k_viterbi); both are bit-exact with the reference.  These flags pin one mapping (tests, profiling). */
+#define DABGPU_FLAG_VIT_LANES_ALWAYS 2u
+#define DABGPU_FLAG_VIT_LANES_NEVER 4u
 
 DABGPU_API const char* dabgpu_version(void);
 DABGPU_API const char* dabgpu_last_error(void);

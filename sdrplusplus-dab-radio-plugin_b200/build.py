@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libdabgpu.so")
 SOURCES = ["dabgpu.cu"]
-HEADERS = ["common.cuh", "tables.cuh", "viterbi.cuh", "chan.cuh", "dabplus.cuh", "ofdm.cuh", "ofdm_demod.cuh", "ofdm_host.cuh", os.path.join("..", "..", "include", "dabgpu.h")]
+HEADERS = ["common.cuh", "tables.cuh", "viterbi.cuh", "viterbi_lanes.cuh", "viterbi_lane_core.h", "chan.cuh", "dabplus.cuh", "ofdm.cuh", "ofdm_demod.cuh", "ofdm_host.cuh", os.path.join("..", "..", "include", "dabgpu.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -61,6 +61,27 @@ def build_adapter_check(force: bool = False) -> str:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("g++ failed building tests/host/adapter_check")
     return ADAPTER_BIN
+
+
+LANE_SRC = os.path.join(ROOT, "tests", "host", "lane_core_check.cpp")
+LANE_BIN = os.path.join(ROOT, "tests", "host", "_bin", "lane_core_check")
+
+
+def build_lane_core_check(force: bool = False) -> str:
+    """g++ build of the CPU check of csrc/viterbi_lane_core.h (host emulation of the DPX instructions) against the oracle.
+    Test infrastructure: this is the only binary that links both a product header and oracle/_ref/libdaboracle.so."""
+    ora = os.path.join(ROOT, "oracle", "_ref")
+    deps = [LANE_SRC, os.path.join(CSRC, "viterbi_lane_core.h"), os.path.join(ora, "libdaboracle.so")]
+    if not force and os.path.exists(LANE_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(LANE_BIN) for d in deps):
+        return LANE_BIN
+    os.makedirs(os.path.dirname(LANE_BIN), exist_ok=True)
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas", "-o", LANE_BIN, LANE_SRC,
+           "-L" + ora, "-ldaboracle", "-Wl,-rpath," + ora]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building tests/host/lane_core_check")
+    return LANE_BIN
 
 
 if __name__ == "__main__":

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "tables.cuh"
 #include "viterbi.cuh"
+#include "viterbi_lanes.cuh"
 #include "chan.cuh"
 #include "dabplus.cuh"
 #include "ofdm_host.cuh"
@@ -30,6 +31,14 @@ struct dabgpu_ctx {
     int vit_blocks = 0;
     size_t prbs_words = 0;
     DevBuf d_vsoft, d_vout, d_verr;   // staging of dabgpu_viterbi_decode
+    // lane-per-trellis batch path (viterbi_lanes.cuh)
+    DevBuf d_vlplan, d_vllist, d_vlsym, d_vlscratch;
+    int vl_mode = 0;                  // 0 auto, 1 always, 2 never
+    uint32_t vl_min_jobs = 6144;      // auto: lanes from this many active trellises per call
+    int vl_blocks = 0;
+    uint32_t vl_scratch_rows = 0;
+    struct { int first = -1, n = -1; uint64_t epoch = 0; uint32_t count[VL_BUCKETS]; uint32_t max_steps = 0; } vl_cache;
+    uint64_t cfg_epoch = 1;
 
     // soft-bit frame ring + channel decode state
     DevBuf d_frames, d_frames_written, d_frames_decoded, d_frame_info;
@@ -169,6 +178,15 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
         if (e != cudaSuccess) { rc = set_error(DABGPU_ERR_CUDA, "cudaFuncSetAttribute(k_viterbi): %s", cudaGetErrorString(e)); dabgpu_ctx_destroy(ctx); return rc; }
     }
     TRY_OR_FREE(ensure_scratch(ctx, 1600));
+    // lane-per-trellis batch path: one CTA of 4 warps per SM (one warp per SM sub-partition: the ACS loop is pipe bound)
+    ctx->vl_blocks = ctx->num_sms;
+    TRY_OR_FREE(ctx->d_vlplan.alloc(sizeof(VlPlan)));
+    ctx->vl_mode = (cfg->flags & DABGPU_FLAG_VIT_LANES_ALWAYS) ? 1 : ((cfg->flags & DABGPU_FLAG_VIT_LANES_NEVER) ? 2 : 0);
+    if (const char* e = getenv("DABGPU_VIT_LANES")) {   // test hook: run every Viterbi call through one mapping
+        if (!strcmp(e, "always")) ctx->vl_mode = 1;
+        else if (!strcmp(e, "never")) ctx->vl_mode = 2;
+    }
+    if (const char* e = getenv("DABGPU_VIT_LANE_CTAS_PER_SM")) { const int k = atoi(e); if (k >= 1 && k <= 4) ctx->vl_blocks = ctx->num_sms * k; }
 
     // frame ring + channel decode buffers
     const size_t frame_bits = size_t(P.nb_frame_bits);
@@ -255,7 +273,7 @@ void dabgpu_ctx_destroy(dabgpu_ctx* ctx) {
     if (ctx->s_d2h) { cudaStreamSynchronize(ctx->s_d2h); cudaStreamDestroy(ctx->s_d2h); }
     ofdm_destroy(ctx->ofdm);
     dabplus_destroy(ctx->dabplus);
-    DevBuf* bufs[] = {&ctx->d_prbs, &ctx->d_counter, &ctx->d_scratch, &ctx->d_jobs, &ctx->d_vsoft, &ctx->d_vout, &ctx->d_verr,
+    DevBuf* bufs[] = {&ctx->d_vlplan, &ctx->d_vllist, &ctx->d_vlsym, &ctx->d_vlscratch, &ctx->d_prbs, &ctx->d_counter, &ctx->d_scratch, &ctx->d_jobs, &ctx->d_vsoft, &ctx->d_vout, &ctx->d_verr,
                       &ctx->d_frames, &ctx->d_frames_written, &ctx->d_frames_decoded, &ctx->d_frame_info, &ctx->d_subcfg, &ctx->d_nsubs,
                       &ctx->d_cifs_consumed, &ctx->d_fic_out, &ctx->d_fic_crc, &ctx->d_msc_out, &ctx->d_msc_valid, &ctx->d_status,
                       &ctx->d_counters};
@@ -295,12 +313,72 @@ int dabgpu_profile_read(dabgpu_ctx* ctx, dabgpu_profile* out) {
 // ---------------------------------------------------------------------------------------------
 // Viterbi
 // ---------------------------------------------------------------------------------------------
-static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs) {
+// Host-side upper bound of what a call can contain (per length class), used to size the buffers of the lane path.
+struct VlBound {
+    uint32_t count[VL_BUCKETS];
+    uint32_t max_steps = 0;
+    bool oversize = false;
+    VlBound() { memset(count, 0, sizeof(count)); }
+    void add(uint32_t steps, uint32_t n = 1) {
+        if (steps == 0 || n == 0) return;
+        if (steps >= VL_MAX_STEPS) { oversize = true; return; }
+        count[vl_bucket(steps)] += n;
+        if (steps > max_steps) max_steps = steps;
+    }
+    void totals(uint32_t* rows, uint32_t* groups, uint32_t* active) const {
+        uint64_t r = 0, g = 0, a = 0;
+        for (uint32_t b = 0; b < VL_BUCKETS; b++) {
+            const uint64_t gb = (count[b] + 31u) >> 5;
+            g += gb; r += gb * vl_bucket_rows(b); a += count[b];
+        }
+        *rows = r > 0xFFFFFFFFull ? 0xFFFFFFFFu : uint32_t(r); *groups = uint32_t(g); *active = uint32_t(a);
+    }
+};
+
+static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, const VlBound* bound) {
     CUDA_TRY(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
-    const int blocks = ctx->vit_blocks;
-    ctx->prof.begin(PROF_VITERBI, ctx->stream);
-    k_viterbi<<<blocks, VIT_WARPS_PER_BLOCK * 32, VIT_SMEM_BYTES, ctx->stream>>>(d_jobs, n_jobs, ctx->d_counter.as<int>(), ctx->d_scratch.as<uint2>(),
-                                                                     ctx->scratch_steps, ctx->d_prbs.as<uint32_t>(), ctx->chan.geom);
+    VlPlan* plan = nullptr;
+    uint32_t rows = 0, groups = 0, active = 0;
+    if (bound && !bound->oversize && ctx->vl_mode != 2) {
+        bound->totals(&rows, &groups, &active);
+        // rows * 128 B of symbols: keep the lane path for calls whose symbol matrix stays below 16 GiB
+        if (active > 0 && (ctx->vl_mode == 1 || active >= ctx->vl_min_jobs) && uint64_t(rows) * 128u <= (16ull << 30)) {
+            int rc;
+            const uint32_t need_rows = bound->max_steps + 64u;
+            if (need_rows > ctx->vl_scratch_rows || !ctx->d_vlscratch.p) {
+                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                const uint32_t r = (need_rows + 255u) & ~255u;
+                if ((rc = ctx->d_vlscratch.alloc(size_t(ctx->vl_blocks) * VL_WARPS_PER_BLOCK * r * 32u * sizeof(uint2)))) return rc;
+                ctx->vl_scratch_rows = r;
+            }
+            if (ctx->d_vllist.bytes < size_t(n_jobs) * 4 || ctx->d_vlsym.bytes < size_t(rows) * 128u) CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if ((rc = ctx->d_vllist.alloc(size_t(n_jobs) * 4))) return rc;
+            if ((rc = ctx->d_vlsym.alloc(size_t(rows) * 128u))) return rc;
+            plan = ctx->d_vlplan.as<VlPlan>();
+        }
+    }
+    if (plan) {
+        static const VlConst kc = {0xFFFFFFFFu, 2u, 4u, 16u, 256u, 0x10000u};
+        // planning + time de-interleave / de-puncture pass are accounted as "chan_misc", the decoders as "viterbi"
+        ctx->prof.begin(PROF_CHAN_MISC, ctx->stream);
+        CUDA_TRY(cudaMemsetAsync(plan, 0, sizeof(VlPlan), ctx->stream));
+        const int tb = 256, nb = (n_jobs + tb - 1) / tb;
+        k_vit_count<<<nb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, plan);
+        k_vit_plan<<<1, 32, 0, ctx->stream>>>(plan, ctx->vl_mode, ctx->vl_min_jobs, rows, groups);
+        k_vit_scatter<<<nb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, plan, ctx->d_vllist.as<uint32_t>());
+        k_vit_prep<<<groups, 128, 0, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(), ctx->d_vlsym.as<uint32_t>(), ctx->chan.geom);
+        ctx->prof.end(ctx->stream);
+        ctx->prof.begin(PROF_VITERBI, ctx->stream);
+        k_viterbi_lanes<<<ctx->vl_blocks, VL_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(), ctx->d_vlsym.as<uint32_t>(),
+                                                                                  ctx->d_vlscratch.as<uint2>(), ctx->vl_scratch_rows,
+                                                                                  ctx->d_prbs.as<uint32_t>(), kc);
+        ctx->launches += 5;
+    } else {
+        ctx->prof.begin(PROF_VITERBI, ctx->stream);
+    }
+    // the warp-per-trellis kernel takes the call when the plan says so (few trellises, or no plan at all)
+    k_viterbi<<<ctx->vit_blocks, VIT_WARPS_PER_BLOCK * 32, VIT_SMEM_BYTES, ctx->stream>>>(d_jobs, n_jobs, ctx->d_counter.as<int>(), ctx->d_scratch.as<uint2>(),
+                                                                                       ctx->scratch_steps, ctx->d_prbs.as<uint32_t>(), ctx->chan.geom, reinterpret_cast<const uint32_t*>(plan));
     ctx->prof.end(ctx->stream);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -319,6 +397,7 @@ int dabgpu_viterbi_decode(dabgpu_ctx* ctx, const dabgpu_viterbi_job* jobs, int n
     if ((rc = ctx->d_jobs.alloc(size_t(n_jobs) * sizeof(VitJobDev)))) return rc;
     std::vector<VitJobDev> hj(static_cast<size_t>(n_jobs));
     uint32_t max_steps = 0;
+    VlBound vb;
     for (int i = 0; i < n_jobs; i++) {
         const dabgpu_viterbi_job& j = jobs[i];
         VitJobDev& J = hj[size_t(i)];
@@ -355,12 +434,13 @@ int dabgpu_viterbi_decode(dabgpu_ctx* ctx, const dabgpu_viterbi_job* jobs, int n
         J.out = ctx->d_vout.as<uint8_t>() + j.out_offset;
         J.path_error = ctx->d_verr.as<unsigned long long>() + i;
         if (steps > max_steps) max_steps = steps;
+        vb.add(steps);
     }
     if ((rc = ensure_scratch(ctx, max_steps))) return rc;
     CUDA_TRY(cudaMemcpyAsync(ctx->d_vsoft.p, soft_host, soft_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_jobs.p, hj.data(), hj.size() * sizeof(VitJobDev), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_vout.p, 0, out_bytes, ctx->stream));
-    if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), n_jobs))) return rc;
+    if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), n_jobs, &vb))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_vout.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (path_error_host) CUDA_TRY(cudaMemcpyAsync(path_error_host, ctx->d_verr.p, size_t(n_jobs) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -435,6 +515,7 @@ int dabgpu_msc_configure(dabgpu_ctx* ctx, int stream, const dabgpu_subchannel* s
     CUDA_TRY(cudaMemset(ctx->d_cifs_consumed.as<uint32_t>() + size_t(stream) * ctx->max_subs, 0, size_t(ctx->max_subs) * 4));
     if ((rc = dabplus_reset_stream(ctx->dabplus, stream))) return rc;
     ctx->subs[size_t(stream)] = hs;
+    ctx->cfg_epoch++;
     return DABGPU_OK;
 }
 
@@ -471,7 +552,22 @@ int dabgpu_chan_decode(dabgpu_ctx* ctx, int first, int n) {
     k_chan_build_jobs<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->chan, ctx->d_jobs.as<VitJobDev>(), first, n);
     ctx->prof.end(ctx->stream);
     ctx->launches++;
-    if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), int(total)))) return rc;
+    if (ctx->vl_cache.first != first || ctx->vl_cache.n != n || ctx->vl_cache.epoch != ctx->cfg_epoch) {
+        VlBound vb;
+        for (int s = first; s < first + n; s++) {
+            if (ctx->chan.fic_enabled) vb.add(774u, uint32_t(ctx->P.nb_cifs));
+            for (const SubHost& h : ctx->subs[size_t(s)]) vb.add(uint32_t(h.sched.total_steps()), uint32_t(ctx->P.nb_cifs));
+        }
+        memcpy(ctx->vl_cache.count, vb.count, sizeof(vb.count));
+        ctx->vl_cache.max_steps = vb.max_steps;
+        ctx->vl_cache.first = first; ctx->vl_cache.n = n; ctx->vl_cache.epoch = ctx->cfg_epoch;
+    }
+    {
+        VlBound vb;
+        memcpy(vb.count, ctx->vl_cache.count, sizeof(vb.count));
+        vb.max_steps = ctx->vl_cache.max_steps;
+        if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), int(total), &vb))) return rc;
+    }
     if ((rc = dabplus_run(ctx->dabplus, ctx->chan, first, n, ctx->stream, &ctx->launches, ctx->prof))) return rc;
     ctx->prof.begin(PROF_CHAN_MISC, ctx->stream);
     k_chan_finish<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->chan, first, n);
@@ -574,7 +670,11 @@ int dabgpu_fic_decode(dabgpu_ctx* ctx, const int8_t* soft_host, int n_groups, ui
     }
     CUDA_TRY(cudaMemcpyAsync(ctx->d_vsoft.p, soft_host, n * 2304, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_jobs.p, hj.data(), n * sizeof(VitJobDev), cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), n_groups))) return rc;
+    {
+        VlBound vb;
+        vb.add(774u, uint32_t(n_groups));
+        if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), n_groups, &vb))) return rc;
+    }
     std::vector<uint8_t> tmp(n * (FIC_GROUP_BYTES + 4));
     CUDA_TRY(cudaMemcpyAsync(tmp.data(), ctx->d_vout.p, tmp.size(), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -366,7 +366,9 @@ __device__ void vit_decode_job(const VitJobDev& J, uint2* __restrict__ dec, uint
 // Persistent kernel: every warp pulls trellises from a global counter until none are left.
 __global__ void __launch_bounds__(VIT_WARPS_PER_BLOCK * 32)
 k_viterbi(const VitJobDev* __restrict__ jobs, const int n_jobs, int* __restrict__ counter, uint2* __restrict__ scratch,
-          const uint32_t scratch_steps, const uint32_t* __restrict__ prbs_words, const GatherGeom G) {
+          const uint32_t scratch_steps, const uint32_t* __restrict__ prbs_words, const GatherGeom G, const uint32_t* __restrict__ lanes_plan) {
+    // lanes_plan[0] != 0: this call is decoded by k_viterbi_lanes (viterbi_lanes.cuh), decided on the device by k_vit_plan
+    if (lanes_plan != nullptr && lanes_plan[0] != 0u) return;
     extern __shared__ __align__(16) uint8_t s_vit[];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t wib = threadIdx.x >> 5;

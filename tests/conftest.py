@@ -64,4 +64,14 @@ def gpu_ctx(dab):
     return dab
 
 
+# Viterbi mapping pinned through dabgpu_config.flags: auto (device-side choice by batch size), every call on the
+# lane-per-trellis kernel, every call on the warp-per-trellis kernel.  All three must give the reference's bits.
+VIT_LANES_ALWAYS, VIT_LANES_NEVER = 2, 4
+
+
+@pytest.fixture(params=[0, VIT_LANES_ALWAYS, VIT_LANES_NEVER], ids=["vit-auto", "vit-lanes", "vit-warps"])
+def vit_flags(request):
+    return request.param
+
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")

@@ -33,10 +33,10 @@ def _mk_trellis_cases(tx, rng, n):
     return softs, segs
 
 
-def test_viterbi_matches_oracles(gpu_ctx, tx, pyref):
+def test_viterbi_matches_oracles(gpu_ctx, tx, pyref, vit_flags):
     rng = np.random.default_rng(11)
     softs, segs = _mk_trellis_cases(tx, rng, 160)
-    g = gpu_ctx.DabGpu(mode=1, max_streams=1)
+    g = gpu_ctx.DabGpu(mode=1, max_streams=1, flags=vit_flags)
     outs, perr = g.viterbi_decode(softs, segs)
     port = pyref.PortViterbi()
     ref = pyref.RefViterbi() if pyref.ref_available() else None
@@ -51,7 +51,7 @@ def test_viterbi_matches_oracles(gpu_ctx, tx, pyref):
     g.close()
 
 
-def test_viterbi_long_trellis_and_renormalisation(gpu_ctx, tx, pyref):
+def test_viterbi_long_trellis_and_renormalisation(gpu_ctx, tx, pyref, vit_flags):
     # 864 CU at EEP 4-A: 27654 steps; noisy input forces several renormalisations
     rng = np.random.default_rng(12)
     sg = tx.eep_segments(864, 3, False)
@@ -63,7 +63,7 @@ def test_viterbi_long_trellis_and_renormalisation(gpu_ctx, tx, pyref):
     softs = [tx.hard_to_soft(enc, rng, snr_db=-3.0), rng.integers(-128, 128, size=n_in).astype(np.int8),
              rng.integers(-127, 128, size=n_in).astype(np.int8), (rng.integers(-1, 2, size=n_in) * 127).astype(np.int8),
              np.where(rng.random(n_in) < 0.5, -127, 127).astype(np.int8), tx.hard_to_soft(enc, rng, snr_db=8.0)]
-    g = gpu_ctx.DabGpu(mode=1, max_streams=1)
+    g = gpu_ctx.DabGpu(mode=1, max_streams=1, flags=vit_flags)
     outs, perr = g.viterbi_decode(softs, [sg] * len(softs), descramble=True)
     port = pyref.PortViterbi()
     prbs = pyref.port_scrambler_bytes(outs[0].size)
@@ -94,12 +94,12 @@ def _subs(tx):
 
 
 @pytest.mark.parametrize("snr_db", [None, 4.0])
-def test_frame_decode_fic_msc_dabplus(gpu_ctx, tx, pyref, snr_db):
+def test_frame_decode_fic_msc_dabplus(gpu_ctx, tx, pyref, snr_db, vit_flags):
     """Soft-bit frames in -> FIBs, sub-channel bytes, superframe events out; two streams with different seeds."""
     rng = np.random.default_rng(21)
     subs = _subs(tx)
     n_streams, n_frames = 2, 12
-    g = gpu_ctx.DabGpu(mode=1, max_streams=n_streams)
+    g = gpu_ctx.DabGpu(mode=1, max_streams=n_streams, flags=vit_flags)
     enss = [tx.EnsembleTx(1, subs, seed=100 + s) for s in range(n_streams)]
     use_ref = pyref.ref_available()
     mk_msc = (lambda sc: pyref.RefMsc(sc.start_address, sc.length, sc.is_uep, sc.uep_index, sc.eep_level, sc.eep_type_b)) if use_ref else \

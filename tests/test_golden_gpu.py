@@ -13,10 +13,10 @@ def _load(name):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 
 
-def test_gpu_viterbi_golden(gpu_ctx):
+def test_gpu_viterbi_golden(gpu_ctx, vit_flags):
     z = _load("viterbi_kat.npz")
     keys = sorted(k[:-5] for k in z.files if k.endswith("_soft"))
-    g = gpu_ctx.DabGpu(mode=1, max_streams=1)
+    g = gpu_ctx.DabGpu(mode=1, max_streams=1, flags=vit_flags)
     outs, perr = g.viterbi_decode([z[k + "_soft"] for k in keys], [[tuple(int(v) for v in r) for r in z[k + "_segs"]] for k in keys])
     for i, k in enumerate(keys):
         assert np.array_equal(outs[i], z[k + "_out"]), k
@@ -24,11 +24,11 @@ def test_gpu_viterbi_golden(gpu_ctx):
     g.close()
 
 
-def test_gpu_channel_chain_golden(gpu_ctx, tx):
+def test_gpu_channel_chain_golden(gpu_ctx, tx, vit_flags):
     z = _load("channel_kat.npz")
     subs = [tx.Subchannel(i, int(s[0]), int(s[1]), bool(s[2]), int(s[3]), int(s[4]), bool(s[5]), bool(s[6])) for i, s in enumerate(z["subs"])]
     used = int(z["used_bits"][0])
-    g = gpu_ctx.DabGpu(mode=1, max_streams=1)
+    g = gpu_ctx.DabGpu(mode=1, max_streams=1, flags=vit_flags)
     g.msc_configure(0, subs)
     fib_counts, fibs = z["fib_counts"], z["fibs"]
     fpos, gi, out_idx = 0, 0, 0
