@@ -73,20 +73,28 @@ template <int N, int FMT> struct DemodCfg {
 // quantisation of t at |t| ~ 1e3 cycles dominates the reference's own phase noise -- while sin/cos of the wrapped
 // phase come from the SFU (sin.approx, |err| < 5e-7) instead of the 6-term Chebyshev polynomial.
 //   nf = float(n & ~3), kf = float(n & 3) * f, kf25 = kf + 0.25f
+// round to nearest even by the 1.5 * 2^23 trick (two FADDs on the FMA pipe instead of FRND on the quarter-rate XU pipe);
+// identical to rintf for |t| < 2^22, and |t| stays below a few thousand cycles here
+__device__ __forceinline__ float pll_rint(const float t) { return __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f); }
+
 __device__ __forceinline__ float2 pll_rotate_sfu(const float2 v, const float nf, const float kf, const float kf25, const float f, const float dt0) {
     const float base = __fmaf_rn(nf, f, dt0);
     float ts = __fadd_rn(base, kf);
     float tc = __fadd_rn(base, kf25);
-    ts = __fsub_rn(ts, rintf(ts));
-    tc = __fsub_rn(tc, rintf(tc));
+    ts = __fsub_rn(ts, pll_rint(ts));
+    tc = __fsub_rn(tc, pll_rint(tc));
     const float sn = __sinf(ts * 6.283185307179586f), cs = __sinf(tc * 6.283185307179586f);
     return make_float2(__fmaf_rn(cs, v.x, -__fmul_rn(sn, v.y)), __fmaf_rn(cs, v.y, __fmul_rn(sn, v.x)));
 }
 
 template <int FMT> __device__ __forceinline__ float2 demod_raw_to_c32(const uint8_t* p) {
     if (FMT == DABGPU_IQ_U8) {
-        const uchar2 v = *reinterpret_cast<const uchar2*>(p);
-        return make_float2(__fmul_rn(__fsub_rn(float(v.x), 127.5f), 1.0f / 127.5f), __fmul_rn(__fsub_rn(float(v.y), 127.5f), 1.0f / 127.5f));
+        // (u8 - 127.5) * (1/127.5) as the reference computes it (app_iq_readers.h:19-27), with the u8 -> f32 conversion done
+        // by placing the byte in the mantissa of 2^15 (PRMT, ALU pipe) instead of I2F (XU pipe): 32768 + b - 32895.5 is exact
+        const uint32_t v = *reinterpret_cast<const uint16_t*>(p);
+        const float fx = __uint_as_float(__byte_perm(v, 0x47000000u, 0x7404));
+        const float fy = __uint_as_float(__byte_perm(v, 0x47000000u, 0x7414));
+        return make_float2(__fmul_rn(__fsub_rn(fx, 32895.5f), 1.0f / 127.5f), __fmul_rn(__fsub_rn(fy, 32895.5f), 1.0f / 127.5f));
     }
     return *reinterpret_cast<const float2*>(p);
 }
