@@ -1,0 +1,17 @@
+# both launch shapes of k_viterbi_lanes: parity tests with each shape forced, full-chain bench at 256 and 1024 streams
+cd $GRAFT_REPO_ROOT
+TAG=${1:-w}
+(timeout 600 python -m pytest tests/test_channel_gpu.py tests/test_golden_gpu.py tests/test_adapters_gpu.py -m gpu -x -q 2>&1 | tail -4) > gpurun_out/${TAG}_pytest.log 2>&1
+(DABGPU_VIT_LANE_CTAS_PER_SM=4 timeout 600 python -m pytest tests/test_channel_gpu.py tests/test_golden_gpu.py -m gpu -x -q 2>&1 | tail -4) > gpurun_out/${TAG}_pytest_wide.log 2>&1
+(timeout 600 python bench.py --workload full --steps 60 --no-cpu-baseline --e2e-steps 4 2>&1 | tail -1) > gpurun_out/${TAG}_bench_full_256.json 2>&1
+(timeout 600 python bench.py --workload full --streams 1024 --steps 24 --no-cpu-baseline --e2e-steps 4 2>&1 | tail -1) > gpurun_out/${TAG}_bench_full_1024.json 2>&1
+(DABGPU_VIT_LANE_CTAS_PER_SM=1 timeout 600 python bench.py --workload full --streams 1024 --steps 24 --no-cpu-baseline --e2e-steps 4 2>&1 | tail -1) > gpurun_out/${TAG}_bench_full_1024_narrow.json 2>&1
+cat gpurun_out/${TAG}_pytest.log gpurun_out/${TAG}_pytest_wide.log; python - <<PY
+import json
+for f in ('bench_full_256','bench_full_1024','bench_full_1024_narrow'):
+    try:
+        d=json.loads(open('gpurun_out/${TAG}_'+f+'.json').read().strip().splitlines()[-1])
+        print(f,'value',round(d['value'],1),'ms/step',round(d['ms_per_step'],4),'kernel_ms/step',{k:round(v/d['steps'],4) for k,v in d['kernel_ms'].items()},'vit_mbit',round(d.get('viterbi_mbit_s',0),1), 'e2e', round(d['e2e']['value'],1))
+    except Exception as e:
+        print(f,'FAILED',e, open('gpurun_out/${TAG}_'+f+'.json').read()[-600:])
+PY

@@ -35,7 +35,8 @@ struct dabgpu_ctx {
     DevBuf d_vlplan, d_vllist, d_vlsym, d_vlscratch;
     int vl_mode = 0;                  // 0 auto, 1 always, 2 never
     uint32_t vl_min_jobs = 6144;      // auto: lanes from this many active trellises per call
-    int vl_blocks = 0;
+    uint32_t vl_scratch_slots = 0;    // decoder warps the decision scratch is sized for
+    int vl_ctas_forced = 0;           // test hook: 1 or 4 CTAs per SM regardless of the call size
     uint32_t vl_scratch_rows = 0;
     struct { int first = -1, n = -1; uint64_t epoch = 0; uint32_t count[VL_BUCKETS]; uint32_t max_steps = 0; } vl_cache;
     uint64_t cfg_epoch = 1;
@@ -178,15 +179,13 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
         if (e != cudaSuccess) { rc = set_error(DABGPU_ERR_CUDA, "cudaFuncSetAttribute(k_viterbi): %s", cudaGetErrorString(e)); dabgpu_ctx_destroy(ctx); return rc; }
     }
     TRY_OR_FREE(ensure_scratch(ctx, 1600));
-    // lane-per-trellis batch path: one CTA of 4 warps per SM (one warp per SM sub-partition: the ACS loop is pipe bound)
-    ctx->vl_blocks = ctx->num_sms;
     TRY_OR_FREE(ctx->d_vlplan.alloc(sizeof(VlPlan)));
     ctx->vl_mode = (cfg->flags & DABGPU_FLAG_VIT_LANES_ALWAYS) ? 1 : ((cfg->flags & DABGPU_FLAG_VIT_LANES_NEVER) ? 2 : 0);
     if (const char* e = getenv("DABGPU_VIT_LANES")) {   // test hook: run every Viterbi call through one mapping
         if (!strcmp(e, "always")) ctx->vl_mode = 1;
         else if (!strcmp(e, "never")) ctx->vl_mode = 2;
     }
-    if (const char* e = getenv("DABGPU_VIT_LANE_CTAS_PER_SM")) { const int k = atoi(e); if (k >= 1 && k <= 4) ctx->vl_blocks = ctx->num_sms * k; }
+    if (const char* e = getenv("DABGPU_VIT_LANE_CTAS_PER_SM")) { const int k = atoi(e); if (k == 1 || k == 4) ctx->vl_ctas_forced = k; }
 
     // frame ring + channel decode buffers
     const size_t frame_bits = size_t(P.nb_frame_bits);
@@ -339,17 +338,22 @@ static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, 
     CUDA_TRY(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
     VlPlan* plan = nullptr;
     uint32_t rows = 0, groups = 0, active = 0;
+    bool lanes_wide = false;
     if (bound && !bound->oversize && ctx->vl_mode != 2) {
         bound->totals(&rows, &groups, &active);
         // rows * 128 B of symbols: keep the lane path for calls whose symbol matrix stays below 16 GiB
         if (active > 0 && (ctx->vl_mode == 1 || active >= ctx->vl_min_jobs) && uint64_t(rows) * 128u <= (16ull << 30)) {
             int rc;
             const uint32_t need_rows = bound->max_steps + 64u;
-            if (need_rows > ctx->vl_scratch_rows || !ctx->d_vlscratch.p) {
+            lanes_wide = ctx->vl_ctas_forced == 4 || (ctx->vl_ctas_forced == 0 && groups > uint32_t(ctx->num_sms) * VL_WARPS_PER_BLOCK * 2u);
+            const uint32_t need_slots = uint32_t(ctx->num_sms) * VL_WARPS_PER_BLOCK * (lanes_wide ? 4u : 1u);
+            if (need_rows > ctx->vl_scratch_rows || need_slots > ctx->vl_scratch_slots || !ctx->d_vlscratch.p) {
                 CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-                const uint32_t r = (need_rows + 255u) & ~255u;
-                if ((rc = ctx->d_vlscratch.alloc(size_t(ctx->vl_blocks) * VL_WARPS_PER_BLOCK * r * 32u * sizeof(uint2)))) return rc;
+                const uint32_t r = std::max((need_rows + 255u) & ~255u, ctx->vl_scratch_rows);
+                const uint32_t sl = std::max(need_slots, ctx->vl_scratch_slots);
+                if ((rc = ctx->d_vlscratch.alloc(size_t(sl) * r * 32u * sizeof(uint2)))) return rc;
                 ctx->vl_scratch_rows = r;
+                ctx->vl_scratch_slots = sl;
             }
             if (ctx->d_vllist.bytes < size_t(n_jobs) * 4 || ctx->d_vlsym.bytes < size_t(rows) * 128u) CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             if ((rc = ctx->d_vllist.alloc(size_t(n_jobs) * 4))) return rc;
@@ -369,9 +373,15 @@ static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, 
         k_vit_prep<<<groups, 128, 0, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(), ctx->d_vlsym.as<uint32_t>(), ctx->chan.geom);
         ctx->prof.end(ctx->stream);
         ctx->prof.begin(PROF_VITERBI, ctx->stream);
-        k_viterbi_lanes<<<ctx->vl_blocks, VL_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(), ctx->d_vlsym.as<uint32_t>(),
-                                                                                  ctx->d_vlscratch.as<uint2>(), ctx->vl_scratch_rows,
-                                                                                  ctx->d_prbs.as<uint32_t>(), kc);
+        if (!lanes_wide) {
+            k_viterbi_lanes<40u, 1><<<ctx->num_sms, VL_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(), ctx->d_vlsym.as<uint32_t>(),
+                                                                                            ctx->d_vlscratch.as<uint2>(), ctx->vl_scratch_rows,
+                                                                                            ctx->d_prbs.as<uint32_t>(), kc);
+        } else {
+            k_viterbi_lanes<10u, 4><<<ctx->num_sms * 4, VL_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(), ctx->d_vlsym.as<uint32_t>(),
+                                                                                                ctx->d_vlscratch.as<uint2>(), ctx->vl_scratch_rows,
+                                                                                                ctx->d_prbs.as<uint32_t>(), kc);
+        }
         ctx->launches += 5;
     } else {
         ctx->prof.begin(PROF_VITERBI, ctx->stream);

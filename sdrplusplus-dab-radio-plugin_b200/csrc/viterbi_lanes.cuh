@@ -20,7 +20,6 @@
 #define VL_BUCKETS 64
 #define VL_MAX_STEPS 73728u   // longest trellis the length classes cover (a full CIF at the weakest code is < 50 000 steps)
 #define VL_PAD_ROWS 16u       // rounding to the unroll factor + one prefetched iteration
-#define VL_TB_BLOCK 40u       // traceback rows fetched per batch (multiple of VL_UNROLL), two batches in flight
 
 __host__ __device__ inline uint32_t vl_bucket(uint32_t steps) { return steps < 8192u ? (steps >> 8) : 32u + ((steps - 8192u) >> 11); }
 // exclusive upper bound of the trellis lengths of a class
@@ -80,14 +79,18 @@ __global__ void k_vit_scatter(const VitJobDev* __restrict__ jobs, const int n_jo
     list[plan->list_base[b] + atomicAdd(&plan->cursor[b], 1u)] = uint32_t(gid);
 }
 
-// group index -> class, first list entry, number of trellises, first symbol row
+// group index -> class, first list entry, number of trellises, first symbol row.  Called by whole warps: every lane tests two
+// classes, so the plan is read with one round trip instead of a serial walk over the 64 classes.
 __device__ __forceinline__ void vl_locate(const VlPlan* __restrict__ plan, const uint32_t g, uint32_t& list0, uint32_t& n_in, uint32_t& row0) {
-    uint32_t b = 0;
-#pragma unroll 1
-    for (int i = VL_BUCKETS - 1; i >= 0; --i) {
-        const uint32_t c = plan->count[i];
-        if (c != 0u && g >= plan->group_base[i] && g < plan->group_base[i] + ((c + 31u) >> 5)) { b = uint32_t(i); break; }
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t hit = 0xFFFFFFFFu;
+#pragma unroll
+    for (uint32_t h = 0; h < 2u; h++) {
+        const uint32_t i = lane + 32u * h;
+        const uint32_t c = plan->count[i], gb = plan->group_base[i];
+        if (c != 0u && g >= gb && g < gb + ((c + 31u) >> 5)) hit = i;
     }
+    const uint32_t b = __reduce_min_sync(FULL_MASK, hit) & (VL_BUCKETS - 1u);   // exactly one class contains g
     const uint32_t gi = g - plan->group_base[b];
     list0 = plan->list_base[b] + gi * 32u;
     n_in = min(32u, plan->count[b] - gi * 32u);
@@ -148,9 +151,69 @@ __device__ __forceinline__ void vl_emit_word(uint8_t* __restrict__ out, const ui
     }
 }
 
+// Whole-block traceback from state 0 (viterbi_decoder_core.h:214-236): decoded bit b comes from the decision word of
+// step b + 6.  All lanes walk the same rows (coalesced 256 B loads, two batches of rows in flight); a lane joins when the
+// walk reaches the last decision word it needs.  Then energy dispersal (additive_scrambler.h:10-36) and the FIB CRCs.
+template <uint32_t VL_TB_BLOCK>   // traceback rows fetched per batch (multiple of VL_UNROLL), two batches in flight
+__device__ __forceinline__ void vl_traceback(const uint2* __restrict__ dec, const VitJobDev* __restrict__ J, const bool have, const uint32_t n_out_bytes,
+                                             const uint32_t flags, uint8_t* __restrict__ const out, const uint32_t* __restrict__ prbs_words) {
+    const uint32_t nbits = n_out_bytes * 8u;
+    const uint32_t top = __reduce_max_sync(FULL_MASK, nbits);      // rows top+5 .. 6 are walked
+    if (top != 0u) {
+        uint32_t state = 0, acc = 0;
+        const int first_block = int((top + 5u) / VL_TB_BLOCK);
+        uint2 cur[VL_TB_BLOCK];
+#pragma unroll
+        for (int r = 0; r < int(VL_TB_BLOCK); r++) cur[r] = dec[size_t(uint32_t(first_block) * VL_TB_BLOCK + r) * 32u];
+#pragma unroll 1
+        for (int blk = first_block; blk >= 0; --blk) {
+            uint2 nx[VL_TB_BLOCK];
+            if (blk > 0) {
+#pragma unroll
+                for (int r = 0; r < int(VL_TB_BLOCK); r++) nx[r] = dec[size_t(uint32_t(blk - 1) * VL_TB_BLOCK + r) * 32u];
+            }
+#pragma unroll
+            for (int r = int(VL_TB_BLOCK) - 1; r >= 0; --r) {
+                const uint32_t t = uint32_t(blk) * VL_TB_BLOCK + uint32_t(r);
+                if (t >= 6u && t < nbits + 6u) {
+                    const uint32_t b = t - 6u;
+                    const uint32_t bit = vl_decision(cur[r].x, cur[r].y, state, uint32_t(r) % VL_UNROLL);
+                    state = (state >> 1) | (bit << 5);
+                    acc = (acc >> 1) | (bit << 31);
+                    if ((b & 31u) == 0u) {
+                        const uint32_t widx = b >> 5;
+                        uint32_t v = acc;
+                        if (flags & VJ_DESCRAMBLE) v ^= prbs_words[widx];
+                        vl_emit_word(out, n_out_bytes, widx, v);
+                        acc = 0;
+                    }
+                }
+            }
+            if (blk > 0) {
+#pragma unroll
+                for (int r = 0; r < int(VL_TB_BLOCK); r++) cur[r] = nx[r];
+            }
+        }
+    }
+    if (have && (flags & VJ_FIB_CRC)) {
+        // FIB = 30 data bytes + CRC16, fic_decoder.cpp:98-116
+        for (uint32_t f = 0; f < J->n_fibs; f++) {
+            const uint8_t* fib = out + 32u * f;
+            const uint16_t rx = uint16_t((uint16_t(fib[30]) << 8) | fib[31]);
+            J->crc_ok[f] = (crc16_ccitt_dev(fib, 30) == rx) ? 1 : 0;
+        }
+    }
+}
+
 #define VL_WARPS_PER_BLOCK 4
 
-__global__ void __launch_bounds__(VL_WARPS_PER_BLOCK * 32, 1)
+// Two builds of the same kernel.  <40, 1>: one CTA per SM = one decoder warp per SM sub-partition, for calls with up to one
+// group per warp (256 streams x 76 trellises = 608 groups on 592 warps); the lone warp hides the latency of its traceback
+// loads with 2 x 40 rows in flight (240 registers).  <10, 4>: 128 registers, four CTAs per SM, for larger calls: a single
+// warp issues at most every other cycle, four warps per sub-partition bring the ACS loop from 540 to 300 cycles per step
+// (scripts/micro/lane_fwd.cu) and hide the traceback latency by themselves.
+template <uint32_t TB, int CTAS>
+__global__ void __launch_bounds__(VL_WARPS_PER_BLOCK * 32, CTAS)
 k_viterbi_lanes(const VitJobDev* __restrict__ jobs, VlPlan* __restrict__ plan, const uint32_t* __restrict__ list, const uint32_t* __restrict__ sym,
                 uint2* __restrict__ scratch, const uint32_t scratch_rows, const uint32_t* __restrict__ prbs_words, const VlConst kc) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -197,55 +260,7 @@ k_viterbi_lanes(const VitJobDev* __restrict__ jobs, VlPlan* __restrict__ plan, c
             if (have && J->path_error != nullptr) *J->path_error = final_err;
         }
 
-        // ---- whole-block traceback from state 0 (viterbi_decoder_core.h:214-236): decoded bit b comes from the decision
-        // word of step b + 6.  All lanes walk the same rows (coalesced 256 B loads); a lane joins when the walk reaches
-        // the last decision word it needs.
-        const uint32_t nbits = n_out_bytes * 8u;
-        const uint32_t top = __reduce_max_sync(FULL_MASK, nbits);      // rows top+5 .. 6 are walked
-        if (top != 0u) {
-            uint32_t state = 0, acc = 0;
-            const int first_block = int((top + 5u) / VL_TB_BLOCK);
-            uint2 cur[VL_TB_BLOCK];
-#pragma unroll
-            for (int r = 0; r < int(VL_TB_BLOCK); r++) cur[r] = dec[size_t(uint32_t(first_block) * VL_TB_BLOCK + r) * 32u];
-#pragma unroll 1
-            for (int blk = first_block; blk >= 0; --blk) {
-                uint2 nx[VL_TB_BLOCK];
-                if (blk > 0) {
-#pragma unroll
-                    for (int r = 0; r < int(VL_TB_BLOCK); r++) nx[r] = dec[size_t(uint32_t(blk - 1) * VL_TB_BLOCK + r) * 32u];
-                }
-#pragma unroll
-                for (int r = int(VL_TB_BLOCK) - 1; r >= 0; --r) {
-                    const uint32_t t = uint32_t(blk) * VL_TB_BLOCK + uint32_t(r);
-                    if (t >= 6u && t < nbits + 6u) {
-                        const uint32_t b = t - 6u;
-                        const uint32_t bit = vl_decision(cur[r].x, cur[r].y, state, uint32_t(r) % VL_UNROLL);
-                        state = (state >> 1) | (bit << 5);
-                        acc = (acc >> 1) | (bit << 31);
-                        if ((b & 31u) == 0u) {
-                            const uint32_t widx = b >> 5;
-                            uint32_t v = acc;
-                            if (flags & VJ_DESCRAMBLE) v ^= prbs_words[widx];
-                            vl_emit_word(out, n_out_bytes, widx, v);
-                            acc = 0;
-                        }
-                    }
-                }
-                if (blk > 0) {
-#pragma unroll
-                    for (int r = 0; r < int(VL_TB_BLOCK); r++) cur[r] = nx[r];
-                }
-            }
-        }
-        if (have && (flags & VJ_FIB_CRC)) {
-            // FIB = 30 data bytes + CRC16, fic_decoder.cpp:98-116
-            for (uint32_t f = 0; f < J->n_fibs; f++) {
-                const uint8_t* fib = out + 32u * f;
-                const uint16_t rx = uint16_t((uint16_t(fib[30]) << 8) | fib[31]);
-                J->crc_ok[f] = (crc16_ccitt_dev(fib, 30) == rx) ? 1 : 0;
-            }
-        }
+        vl_traceback<TB>(dec, J, have, n_out_bytes, flags, out, prbs_words);
         __syncwarp();
     }
 }
