@@ -56,6 +56,7 @@ class ClockSampler(threading.Thread):
         self.max_mhz = None
         self.stop_flag = False
         self.source = "nvml"
+        self.ready = threading.Event()   # set after the first sample: the timed region starts only then
 
     def _run_nvml(self):
         import pynvml as nv
@@ -66,6 +67,7 @@ class ClockSampler(threading.Thread):
                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
         while not self.stop_flag:
             self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.ready.set()
             r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
             for n, b in bits.items():
                 if r & b:
@@ -82,6 +84,7 @@ class ClockSampler(threading.Thread):
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip().split(",")
                 self.samples.append(float(out[0]))
+                self.ready.set()
                 self.max_mhz = float(out[1])
                 for n, v in zip(names, out[2:]):
                     if "Active" in v and "Not" not in v:
@@ -314,6 +317,8 @@ def main():
     launches0 = g.launch_count
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.ready.wait(timeout=20)   # NVML initialisation on a fresh box can take longer than the whole timed region
+    sampler.samples.clear()          # keep only what is sampled while the kernels run
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
