@@ -242,6 +242,32 @@ DABGPU_API int dabgpu_msc_configure(dabgpu_ctx* ctx, int stream, const dabgpu_su
 DABGPU_API int dabgpu_softbits_push(dabgpu_ctx* ctx, const int8_t* frames_host, size_t stream_stride_bytes,
                                     int first_stream, int n_streams);
 
+/* ---------------------------------------------------------------------------------------------
+ * Self-configuration from the FIC (host only, no GPU work): the FIG 0/1, 0/2, 0/3 and 0/14 subset of
+ *   FIG_Processor::ProcessFIB          dab/fic/fig_processor.cpp:94-152, 302-551
+ *   Radio_FIG_Handler                  dab/radio_fig_handler.cpp:35-214, 474-481
+ *   DAB_Database_Updater (first value of a field wins, required-field masks)  dab/database/dab_database_updater.cpp:94-228
+ *   BasicRadio::UpdateAfterProcessing  basic_radio/basic_radio.cpp:83-154 (which sub-channels get a decoder)
+ * implemented in sdrplusplus-dab-radio-plugin_b200/host/fic_autoconfig.hpp.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dabgpu_autocfg dabgpu_autocfg;
+DABGPU_API dabgpu_autocfg* dabgpu_autocfg_create(void);
+DABGPU_API void dabgpu_autocfg_destroy(dabgpu_autocfg* a);
+/* n_fibs FIBs of `stride` bytes each (30 data bytes are read); crc_ok may be NULL (all valid).  Returns the number of
+ * FIBs that changed the database, or a negative dabgpu_status. */
+DABGPU_API int dabgpu_autocfg_push_fibs(dabgpu_autocfg* a, const uint8_t* fibs, int n_fibs, size_t stride, const uint8_t* crc_ok);
+/* Database dump, rows of int32.  Sub-channels: id, start, length, is_uep, uep_index, eep_level, eep_type (255 = unset),
+ * fec_scheme (255 = unset), is_complete.  Components: service id, id type (0 = 16 bit, 1 = 32 bit), component id,
+ * sub-channel, global id, transport mode, audio type, data type, packet address, is_complete. */
+#define DABGPU_AUTOCFG_SUB_COLS 9
+#define DABGPU_AUTOCFG_COMP_COLS 10
+DABGPU_API int dabgpu_autocfg_dump(dabgpu_autocfg* a, int32_t* subs, int subs_cap_rows, int* n_subs, int32_t* comps, int comps_cap_rows, int* n_comps);
+/* The sub-channels BasicRadio would attach an audio decoder to, in database order; ids[i] = SubChId of out[i]. */
+DABGPU_API int dabgpu_autocfg_runnable(dabgpu_autocfg* a, dabgpu_subchannel* out, uint8_t* ids, int cap, int* n_out);
+/* dabgpu_msc_configure(ctx, stream, runnable set) when the set differs from the one applied last; returns 1 if it
+ * reconfigured, 0 if nothing changed, negative on error. */
+DABGPU_API int dabgpu_autocfg_apply(dabgpu_autocfg* a, dabgpu_ctx* ctx, int stream);
+
 /* Decodes, for every stream in [first, first+n), the oldest frame in its ring that has not been
  * channel-decoded yet (streams without one are skipped).  Results stay on the device until fetched. */
 DABGPU_API int dabgpu_chan_decode(dabgpu_ctx* ctx, int first_stream, int n_streams);

@@ -103,6 +103,13 @@ class RefLib:
                                             np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
             L.ref_time_chain_u8.restype = C.c_double
 
+        if hasattr(L, "ref_fig_create"):
+            L.ref_fig_create.restype = C.c_void_p
+            L.ref_fig_destroy.argtypes = [C.c_void_p]
+            L.ref_fig_process_fib.argtypes = [C.c_void_p, _u8p]
+            L.ref_fig_dump.argtypes = [C.c_void_p, _i32p, C.c_int, _i32p, C.c_int, C.POINTER(C.c_int)]
+            L.ref_fig_dump.restype = C.c_int
+
     def build_info(self) -> str:
         return self.L.ref_build_info().decode()
 
@@ -250,6 +257,32 @@ class RefAac:
         n = self.lib.ref_aac_process(self.h, frame, frame.size, self.log, self.log.size)
         assert n <= self.log.size
         return parse_event_log(self.log[:n].tobytes())
+
+
+class RefFig:
+    """FIG_Processor -> Radio_FIG_Handler -> DAB_Database_Updater of the reference; dump() returns (subchannels, components)
+    in the row formats of dabgpu_autocfg_dump."""
+
+    def __init__(self):
+        self.L = RefLib.get().L
+        self.h = self.L.ref_fig_create()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_fig_destroy(self.h)
+            self.h = None
+
+    def process_fib(self, fib: np.ndarray):
+        fib = np.ascontiguousarray(fib[:30], dtype=np.uint8)
+        assert fib.size == 30
+        self.L.ref_fig_process_fib(self.h, fib)
+
+    def dump(self):
+        subs = np.zeros((64, 9), dtype=np.int32)
+        comps = np.zeros((256, 10), dtype=np.int32)
+        nc = C.c_int(0)
+        ns = self.L.ref_fig_dump(self.h, subs.reshape(-1), 64, comps.reshape(-1), 256, C.byref(nc))
+        return subs[:ns].copy(), comps[:nc.value].copy()
 
 
 class RefOfdm:

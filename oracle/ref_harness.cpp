@@ -553,3 +553,51 @@ API double ref_time_chain_u8(int mode, const uint8_t* iq, long n_samples, int bl
     ref_ofdm_destroy(r);
     return std::chrono::duration<double>(t1-t0).count();
 }
+
+// ---- FIG processing: FIBs -> the reference's database --------------------------------
+// FIG_Processor (dab/fic/fig_processor.h) -> Radio_FIG_Handler (dab/radio_fig_handler.h) -> DAB_Database_Updater
+// (dab/database/dab_database_updater.h), exactly the chain BasicFICRunner builds (basic_radio/basic_fic_runner.cpp:9-32).
+#include "dab/fic/fig_processor.h"
+#include "dab/radio_fig_handler.h"
+#include "dab/dab_misc_info.h"
+#include "dab/database/dab_database.h"
+#include "dab/database/dab_database_updater.h"
+
+struct RefFig {
+    FIG_Processor proc;
+    Radio_FIG_Handler handler;
+    DAB_Database_Updater updater;
+    DAB_Misc_Info misc;
+    RefFig() {
+        handler.SetUpdater(&updater);
+        handler.SetMiscInfo(&misc);
+        proc.SetHandler(&handler);
+    }
+};
+
+API void* ref_fig_create() { return new RefFig(); }
+API void ref_fig_destroy(void* p) { delete (RefFig*)p; }
+API void ref_fig_process_fib(void* p, const uint8_t* fib30) { ((RefFig*)p)->proc.ProcessFIB({fib30, size_t(30)}); }
+// same row formats as dabgpu_autocfg_dump (include/dabgpu.h)
+API int ref_fig_dump(void* p, int32_t* subs, int subs_cap, int32_t* comps, int comps_cap, int* n_comps) {
+    const auto& db = ((RefFig*)p)->updater.GetDatabase();
+    int ns = 0;
+    for (const auto& s : db.subchannels) {
+        if (ns >= subs_cap) break;
+        int32_t* r = subs + ns*9;
+        r[0] = s.id; r[1] = s.start_address; r[2] = s.length; r[3] = s.is_uep; r[4] = s.uep_prot_index; r[5] = s.eep_prot_level;
+        r[6] = int(uint8_t(s.eep_type)); r[7] = int(uint8_t(s.fec_scheme)); r[8] = s.is_complete;
+        ns++;
+    }
+    int nc = 0;
+    for (const auto& c : db.service_components) {
+        if (nc >= comps_cap) break;
+        int32_t* r = comps + nc*10;
+        r[0] = int32_t(c.service_id.value); r[1] = int(uint8_t(c.service_id.type)); r[2] = c.component_id; r[3] = c.subchannel_id; r[4] = c.global_id;
+        r[5] = int(uint8_t(c.transport_mode)); r[6] = int(uint8_t(c.audio_service_type)); r[7] = int(uint8_t(c.data_service_type));
+        r[8] = c.packet_address; r[9] = c.is_complete;
+        nc++;
+    }
+    *n_comps = nc;
+    return ns;
+}

@@ -100,6 +100,8 @@ EXPORTS = [
     "dabgpu_chan_get_status", "dabgpu_chan_get_fic", "dabgpu_chan_get_msc", "dabgpu_chan_get_dabplus_events", "dabgpu_rs_decode",
     "dabgpu_get_counters", "dabgpu_submit", "dabgpu_wait", "dabgpu_msc_get_layout",
     "dabgpu_ofdm_set_config", "dabgpu_fic_decode", "dabgpu_dabplus_open", "dabgpu_dabplus_close", "dabgpu_dabplus_process",
+    "dabgpu_autocfg_create", "dabgpu_autocfg_destroy", "dabgpu_autocfg_push_fibs", "dabgpu_autocfg_dump", "dabgpu_autocfg_runnable",
+    "dabgpu_autocfg_apply",
 ]
 
 _lib = None
@@ -154,6 +156,13 @@ def load_library() -> C.CDLL:
     L.dabgpu_submit.argtypes = [C.c_void_p, C.POINTER(Step), C.POINTER(C.c_uint64)]
     L.dabgpu_wait.argtypes = [C.c_void_p, C.c_uint64]
     L.dabgpu_msc_get_layout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.dabgpu_autocfg_create.restype = C.c_void_p
+    L.dabgpu_autocfg_destroy.argtypes = [C.c_void_p]
+    L.dabgpu_autocfg_destroy.restype = None
+    L.dabgpu_autocfg_push_fibs.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]
+    L.dabgpu_autocfg_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    L.dabgpu_autocfg_runnable.argtypes = [C.c_void_p, C.POINTER(SubchannelC), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    L.dabgpu_autocfg_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     _lib = L
     return L
 
@@ -409,3 +418,56 @@ class DabGpu:
         produced = np.zeros(n, dtype=np.uint8)
         _check(self.L.dabgpu_ofdm_fetch_latest(self.h, first_stream, n, _ptr(frames), _ptr(produced)))
         return frames, produced
+
+
+class FicAutoConfig:
+    """Self-configuration from the FIC (host only): FIBs in, sub-channel table out (dabgpu_autocfg_*, include/dabgpu.h).
+    Mirrors FIG_Processor -> Radio_FIG_Handler -> DAB_Database_Updater -> BasicRadio::UpdateAfterProcessing of the reference
+    for FIG 0/1, 0/2, 0/3 and 0/14."""
+
+    def __init__(self):
+        self.L = load_library()
+        self.h = C.c_void_p(self.L.dabgpu_autocfg_create())
+
+    def close(self):
+        if self.h:
+            self.L.dabgpu_autocfg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def push_fibs(self, fibs: np.ndarray, crc_ok: Optional[np.ndarray] = None) -> int:
+        """fibs: (n, >=30) uint8 rows.  Returns how many of them changed the database."""
+        fibs = np.ascontiguousarray(fibs, dtype=np.uint8)
+        if fibs.ndim == 1:
+            fibs = fibs.reshape(1, -1)
+        ok = None if crc_ok is None else np.ascontiguousarray(crc_ok, dtype=np.uint8)
+        rc = self.L.dabgpu_autocfg_push_fibs(self.h, fibs.ctypes.data, fibs.shape[0], fibs.strides[0], None if ok is None else ok.ctypes.data)
+        if rc < 0:
+            _check(rc)
+        return rc
+
+    def dump(self) -> Tuple[np.ndarray, np.ndarray]:
+        subs = np.zeros((64, 9), dtype=np.int32)
+        comps = np.zeros((512, 10), dtype=np.int32)
+        ns, nc = C.c_int(0), C.c_int(0)
+        _check(self.L.dabgpu_autocfg_dump(self.h, subs.ctypes.data, 64, C.byref(ns), comps.ctypes.data, 512, C.byref(nc)))
+        return subs[:ns.value].copy(), comps[:nc.value].copy()
+
+    def runnable(self) -> Tuple[list, list]:
+        arr = (SubchannelC * 64)()
+        ids = np.zeros(64, dtype=np.uint8)
+        n = C.c_int(0)
+        _check(self.L.dabgpu_autocfg_runnable(self.h, arr, ids.ctypes.data, 64, C.byref(n)))
+        out = [{f: getattr(arr[i], f) for f, _ in SubchannelC._fields_} for i in range(n.value)]
+        return out, [int(x) for x in ids[:n.value]]
+
+    def apply(self, ctx: "DabGpu", stream: int = 0) -> bool:
+        rc = self.L.dabgpu_autocfg_apply(self.h, ctx.h, stream)
+        if rc < 0:
+            _check(rc)
+        return rc == 1

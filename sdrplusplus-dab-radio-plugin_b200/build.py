@@ -63,26 +63,5 @@ def build_adapter_check(force: bool = False) -> str:
     return ADAPTER_BIN
 
 
-LANE_SRC = os.path.join(ROOT, "tests", "host", "lane_core_check.cpp")
-LANE_BIN = os.path.join(ROOT, "tests", "host", "_bin", "lane_core_check")
-
-
-def build_lane_core_check(force: bool = False) -> str:
-    """g++ build of the CPU check of csrc/viterbi_lane_core.h (host emulation of the DPX instructions) against the oracle.
-    Test infrastructure: this is the only binary that links both a product header and oracle/_ref/libdaboracle.so."""
-    ora = os.path.join(ROOT, "oracle", "_ref")
-    deps = [LANE_SRC, os.path.join(CSRC, "viterbi_lane_core.h"), os.path.join(ora, "libdaboracle.so")]
-    if not force and os.path.exists(LANE_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(LANE_BIN) for d in deps):
-        return LANE_BIN
-    os.makedirs(os.path.dirname(LANE_BIN), exist_ok=True)
-    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas", "-o", LANE_BIN, LANE_SRC,
-           "-L" + ora, "-ldaboracle", "-Wl,-rpath," + ora]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("g++ failed building tests/host/lane_core_check")
-    return LANE_BIN
-
-
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

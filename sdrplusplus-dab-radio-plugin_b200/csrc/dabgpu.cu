@@ -6,6 +6,7 @@
 #include "chan.cuh"
 #include "dabplus.cuh"
 #include "ofdm_host.cuh"
+#include "../host/fic_autoconfig.hpp"
 
 #define DABGPU_VERSION "dabgpu 0.1 (sm_100a)"
 
@@ -549,6 +550,77 @@ int dabgpu_softbits_push(dabgpu_ctx* ctx, const int8_t* frames_host, size_t stri
     CUDA_TRY(cudaMemcpyAsync(ctx->d_frames_written.as<uint32_t>() + first, written, size_t(n) * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return DABGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Self-configuration from the FIC (host only)
+// ---------------------------------------------------------------------------------------------
+struct dabgpu_autocfg {
+    dabgpu_host::FIC_Autoconfig db;
+    std::vector<dabgpu_subchannel> applied;
+    bool applied_once = false;
+};
+
+dabgpu_autocfg* dabgpu_autocfg_create(void) { return new dabgpu_autocfg(); }
+void dabgpu_autocfg_destroy(dabgpu_autocfg* a) { delete a; }
+
+int dabgpu_autocfg_push_fibs(dabgpu_autocfg* a, const uint8_t* fibs, int n_fibs, size_t stride, const uint8_t* crc_ok) {
+    if (!a || (!fibs && n_fibs > 0)) return set_error(DABGPU_ERR_INVALID, "null argument");
+    if (stride < 30) return set_error(DABGPU_ERR_INVALID, "FIB stride %zu < 30", stride);
+    int changed = 0;
+    for (int i = 0; i < n_fibs; i++) {
+        if (crc_ok && !crc_ok[i]) continue;   // FIC_Decoder only emits FIBs whose CRC matched (fic_decoder.cpp:98-116)
+        if (a->db.ProcessFIB(fibs + size_t(i) * stride, 30)) changed++;
+    }
+    return changed;
+}
+
+int dabgpu_autocfg_dump(dabgpu_autocfg* a, int32_t* subs, int subs_cap_rows, int* n_subs, int32_t* comps, int comps_cap_rows, int* n_comps) {
+    if (!a || !n_subs || !n_comps) return set_error(DABGPU_ERR_INVALID, "null argument");
+    const auto& S = a->db.subchannels();
+    const auto& Cc = a->db.components();
+    *n_subs = int(S.size());
+    *n_comps = int(Cc.size());
+    if ((subs && subs_cap_rows < *n_subs) || (comps && comps_cap_rows < *n_comps)) return set_error(DABGPU_ERR_OVERFLOW, "dump buffers too small");
+    if (subs)
+        for (size_t i = 0; i < S.size(); i++) {
+            const int32_t row[DABGPU_AUTOCFG_SUB_COLS] = {S[i].id, S[i].start_address, S[i].length, S[i].is_uep, S[i].uep_prot_index, S[i].eep_prot_level,
+                                                         S[i].eep_type, S[i].fec_scheme, S[i].is_complete};
+            memcpy(subs + i * DABGPU_AUTOCFG_SUB_COLS, row, sizeof(row));
+        }
+    if (comps)
+        for (size_t i = 0; i < Cc.size(); i++) {
+            const int32_t row[DABGPU_AUTOCFG_COMP_COLS] = {int32_t(Cc[i].service_value), Cc[i].service_type, Cc[i].component_id, Cc[i].subchannel_id, Cc[i].global_id,
+                                                          Cc[i].transport_mode, Cc[i].audio_type, Cc[i].data_type, Cc[i].packet_address, Cc[i].is_complete};
+            memcpy(comps + i * DABGPU_AUTOCFG_COMP_COLS, row, sizeof(row));
+        }
+    return DABGPU_OK;
+}
+
+int dabgpu_autocfg_runnable(dabgpu_autocfg* a, dabgpu_subchannel* out, uint8_t* ids, int cap, int* n_out) {
+    if (!a || !n_out) return set_error(DABGPU_ERR_INVALID, "null argument");
+    std::vector<dabgpu_subchannel> v;
+    std::vector<uint8_t> id;
+    a->db.Runnable(v, id);
+    *n_out = int(v.size());
+    if (out || ids) {
+        if (cap < *n_out) return set_error(DABGPU_ERR_OVERFLOW, "%d runnable sub-channels, room for %d", *n_out, cap);
+        for (size_t i = 0; i < v.size(); i++) { if (out) out[i] = v[i]; if (ids) ids[i] = id[i]; }
+    }
+    return DABGPU_OK;
+}
+
+int dabgpu_autocfg_apply(dabgpu_autocfg* a, dabgpu_ctx* ctx, int stream) {
+    if (!a || !ctx) return set_error(DABGPU_ERR_INVALID, "null argument");
+    std::vector<dabgpu_subchannel> v;
+    std::vector<uint8_t> id;
+    a->db.Runnable(v, id);
+    if (a->applied_once && v.size() == a->applied.size() && (v.empty() || memcmp(v.data(), a->applied.data(), v.size() * sizeof(dabgpu_subchannel)) == 0)) return 0;
+    const int rc = dabgpu_msc_configure(ctx, stream, v.data(), int(v.size()));
+    if (rc) return rc;
+    a->applied = v;
+    a->applied_once = true;
+    return 1;
 }
 
 int dabgpu_chan_decode(dabgpu_ctx* ctx, int first, int n) {

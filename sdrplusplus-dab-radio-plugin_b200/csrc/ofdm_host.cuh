@@ -22,6 +22,7 @@ struct OfdmState {
     // group overlaps the demodulation kernel of the other
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+
     PinnedBuf h_produced;
     std::vector<unsigned long long> h_written;   // absolute samples written per stream (internal ring)
 };
@@ -319,8 +320,12 @@ template <int N, int FMT>
 static int ofdm_run_t(OfdmState& O, int first, int n, int n_samples, int block_size, cudaStream_t cs) {
     // a frame consumes at least frame_samples - CP new samples (fine time offset >= -CP), so at most this many complete
     const int max_frames = n_samples / (O.P.nb_frame_samples - O.P.nb_cyclic_prefix) + 1;
-    // two groups on two CUDA streams (kernel timing by class is only meaningful without the overlap: off when profiling)
-    const bool split = n >= 64 && !O.prof->on && O.aux_stream != nullptr && getenv("DABGPU_NO_OVERLAP") == nullptr;
+    // One group on the caller's stream is the default.  The control kernel is latency bound (about 45 us per launch whether it
+    // walks 128 or 256 streams), so splitting the streams into two groups on two CUDA streams pays its latency twice: measured
+    // 0.420 ms per 256-stream step against 0.399 ms unsplit, and 0.480 ms with the control kernels on high-priority streams
+    // and the second group started one kernel late (profiles/README.md, r1f).  DABGPU_OVERLAP_GROUPS=1 keeps the split for
+    // experiments.
+    const bool split = n >= 64 && !O.prof->on && O.aux_stream != nullptr && getenv("DABGPU_OVERLAP_GROUPS") != nullptr;
     if (!split) {
         ofdm_launch_group<N, FMT>(O, first, n, n_samples, block_size, max_frames, cs);
     } else {

@@ -279,6 +279,22 @@ def fig0_1(subchannels: Sequence[Subchannel]) -> List[bytes]:
     return figs
 
 
+def fig0_2(subchannels: Sequence[Subchannel]) -> List[bytes]:
+    """FIG 0/2 service organisation: one programme service (16-bit SId 0xD100 + SubChId) per sub-channel with a single
+    primary stream-audio component, ASCTy 63 (DAB+) or 0 (DAB) (parser: dab/fic/fig_processor.cpp:364-487)."""
+    figs, body = [], b""
+    for sc in subchannels:
+        sid = 0xD100 + sc.id
+        e = bytes([sid >> 8, sid & 0xFF, 0x01, (0 << 6) | (63 if sc.dabplus else 0), (sc.id << 2) | 0x02])
+        if len(body) + len(e) > 28:
+            figs.append(bytes([(0 << 5) | (len(body) + 1), 0x02]) + body)
+            body = b""
+        body += e
+    if body:
+        figs.append(bytes([(0 << 5) | (len(body) + 1), 0x02]) + body)
+    return figs
+
+
 # --------------------------------------------------------------------------------------------
 # RS(120,110) encoder and DAB+ superframe builder
 # (inverse of dab/audio/aac_frame_processor.cpp:201-362, reed_solomon_decoder.cpp:70-178)
@@ -396,7 +412,7 @@ class EnsembleTx:
         self._sf_buf = {sc.id: np.zeros(0, dtype=np.uint8) for sc in self.subchannels}
         # encoded logical frames history for the interleaver: per sub-channel ring of 16
         self._enc_hist = {sc.id: [np.zeros(sc.nb_bits, dtype=np.uint8) for _ in range(16)] for sc in self.subchannels}
-        self._figs = fig0_1(self.subchannels)
+        self._figs = fig0_1(self.subchannels) + fig0_2(self.subchannels)
         self._fig_pos = 0
 
     def _next_logical_frame(self, sc: Subchannel) -> np.ndarray:

@@ -6,14 +6,16 @@ renormalisation, saturation level) and the traceback are verified bit-exactly he
 the accumulated path error of 1200 trellises (noisy, garbage, ties, +-full scale, bursts, all-punctured; lengths 6..6150).
 """
 import importlib
+import os
 import subprocess
+import sys
 
-from conftest import PKG
+from conftest import ROOT
 
 
 def test_lane_core_matches_oracle(pyref):
-    b = importlib.import_module(PKG + ".build")
-    exe = b.build_lane_core_check()
+    sys.path.insert(0, os.path.join(ROOT, "tests", "host"))
+    exe = importlib.import_module("build_checks").build_lane_core_check()
     res = subprocess.run([exe, "1200"], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
     assert " 0 mismatches" in res.stdout
