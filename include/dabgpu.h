@@ -268,6 +268,21 @@ DABGPU_API int dabgpu_autocfg_runnable(dabgpu_autocfg* a, dabgpu_subchannel* out
  * reconfigured, 0 if nothing changed, negative on error. */
 DABGPU_API int dabgpu_autocfg_apply(dabgpu_autocfg* a, dabgpu_ctx* ctx, int stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Capture file formats of the reference's tools (host only): raw IQ in the reader modes of
+ *   get_iq_file_reader_from_mode_string   vendor/DAB-Radio/examples/app_helpers/app_iq_readers.h:107-159
+ *   QuantisedIQ<T>::to_c32 / QuantisedIQToFloatIQ<T>::read                          app_iq_readers.h:19-87
+ * and hard-byte <-> soft-bit frames
+ *   convert_viterbi_bits_to_bytes / convert_viterbi_bytes_to_bits   app_helpers/app_viterbi_convert_block.h:12-44
+ * implemented in sdrplusplus-dab-radio-plugin_b200/host/capture_formats.hpp.  "raw_u8" and c32 can be fed to
+ * dabgpu_ofdm_process directly; the other modes are converted to c32 here, like the reference's readers do.
+ * ------------------------------------------------------------------------------------------- */
+/* mode: "raw_u8", "raw_s8", "raw_s16l", "raw_s16b", "raw_u16l", "raw_u16b", "raw_s32l", "raw_s32b", "raw_u32l", "raw_u32b",
+ * "raw_f32l", "raw_f32b", "raw_f64l", "raw_f64b".  Writes interleaved float I,Q; *n_floats = components converted. */
+DABGPU_API int dabgpu_iq_convert(const char* mode, const void* raw, size_t n_bytes, float* out_c32, size_t out_cap_floats, size_t* n_floats);
+DABGPU_API int dabgpu_softbits_to_bytes(const int8_t* bits, size_t n_bits, uint8_t* bytes);   /* n_bits multiple of 8 */
+DABGPU_API int dabgpu_bytes_to_softbits(const uint8_t* bytes, size_t n_bytes, int8_t* bits);
+
 /* Decodes, for every stream in [first, first+n), the oldest frame in its ring that has not been
  * channel-decoded yet (streams without one are skipped).  Results stay on the device until fetched. */
 DABGPU_API int dabgpu_chan_decode(dabgpu_ctx* ctx, int first_stream, int n_streams);

@@ -103,6 +103,11 @@ class RefLib:
                                             np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
             L.ref_time_chain_u8.restype = C.c_double
 
+        if hasattr(L, "ref_iq_convert"):
+            L.ref_iq_convert.argtypes = [C.c_char_p, _u8p, C.c_size_t, _f32p, C.c_size_t]
+            L.ref_iq_convert.restype = C.c_long
+            L.ref_softbits_to_bytes.argtypes = [_i8p, C.c_size_t, _u8p]
+            L.ref_bytes_to_softbits.argtypes = [_u8p, C.c_size_t, _i8p]
         if hasattr(L, "ref_fig_create"):
             L.ref_fig_create.restype = C.c_void_p
             L.ref_fig_destroy.argtypes = [C.c_void_p]
@@ -257,6 +262,30 @@ class RefAac:
         n = self.lib.ref_aac_process(self.h, frame, frame.size, self.log, self.log.size)
         assert n <= self.log.size
         return parse_event_log(self.log[:n].tobytes())
+
+
+def ref_iq_convert(mode: str, raw: np.ndarray) -> np.ndarray:
+    """The reference's reader chain (app_iq_readers.h) over a memory buffer -> complex64."""
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    out = np.zeros(raw.size + 8, dtype=np.float32)
+    n = RefLib.get().L.ref_iq_convert(mode.encode(), raw, raw.size, out, out.size)
+    if n < 0:
+        raise ValueError(f"reference rejected mode {mode}")
+    return out[:n].view(np.complex64).copy()
+
+
+def ref_softbits_to_bytes(bits: np.ndarray) -> np.ndarray:
+    bits = np.ascontiguousarray(bits, dtype=np.int8)
+    out = np.zeros(bits.size // 8, dtype=np.uint8)
+    RefLib.get().L.ref_softbits_to_bytes(bits, out.size, out)
+    return out
+
+
+def ref_bytes_to_softbits(b: np.ndarray) -> np.ndarray:
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    out = np.zeros(b.size * 8, dtype=np.int8)
+    RefLib.get().L.ref_bytes_to_softbits(b, b.size, out)
+    return out
 
 
 class RefFig:

@@ -601,3 +601,24 @@ API int ref_fig_dump(void* p, int32_t* subs, int subs_cap, int32_t* comps, int c
     *n_comps = nc;
     return ns;
 }
+
+// ---- capture file formats of the reference's tools -----------------------------------
+// The reference's own reader chain (examples/app_helpers/app_iq_readers.h:75-159) fed from a memory buffer, and its
+// soft-bit <-> hard-byte converters (examples/app_helpers/app_viterbi_convert_block.h:12-44).
+#include "app_helpers/app_iq_readers.h"
+#include "app_helpers/app_viterbi_convert_block.h"
+
+API long ref_iq_convert(const char* mode, const uint8_t* raw, size_t n_bytes, float* out, size_t out_cap_floats) {
+    try {
+        FILE* fp = fmemopen(const_cast<uint8_t*>(raw), n_bytes, "rb");   // the reference's InputFile wraps (and closes) a FILE*
+        if (!fp) return -1;
+        auto file = std::make_shared<InputFile<uint8_t>>(fp);
+        auto reader = get_iq_file_reader_from_mode_string(file, mode);
+        const size_t n = reader->read({reinterpret_cast<std::complex<float>*>(out), out_cap_floats/2});
+        return long(2*n);
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
+API void ref_softbits_to_bytes(const int8_t* bits, size_t n_bytes, uint8_t* bytes) { convert_viterbi_bits_to_bytes({bits, n_bytes*8}, {bytes, n_bytes}); }
+API void ref_bytes_to_softbits(const uint8_t* bytes, size_t n_bytes, int8_t* bits) { convert_viterbi_bytes_to_bits({bytes, n_bytes}, {bits, n_bytes*8}); }

@@ -101,7 +101,7 @@ EXPORTS = [
     "dabgpu_get_counters", "dabgpu_submit", "dabgpu_wait", "dabgpu_msc_get_layout",
     "dabgpu_ofdm_set_config", "dabgpu_fic_decode", "dabgpu_dabplus_open", "dabgpu_dabplus_close", "dabgpu_dabplus_process",
     "dabgpu_autocfg_create", "dabgpu_autocfg_destroy", "dabgpu_autocfg_push_fibs", "dabgpu_autocfg_dump", "dabgpu_autocfg_runnable",
-    "dabgpu_autocfg_apply",
+    "dabgpu_autocfg_apply", "dabgpu_iq_convert", "dabgpu_softbits_to_bytes", "dabgpu_bytes_to_softbits",
 ]
 
 _lib = None
@@ -163,6 +163,9 @@ def load_library() -> C.CDLL:
     L.dabgpu_autocfg_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.dabgpu_autocfg_runnable.argtypes = [C.c_void_p, C.POINTER(SubchannelC), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.dabgpu_autocfg_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.dabgpu_iq_convert.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.dabgpu_softbits_to_bytes.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    L.dabgpu_bytes_to_softbits.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     _lib = L
     return L
 
@@ -471,3 +474,34 @@ class FicAutoConfig:
         if rc < 0:
             _check(rc)
         return rc == 1
+
+
+IQ_FILE_MODES = ["raw_u8", "raw_s8", "raw_s16l", "raw_s16b", "raw_u16l", "raw_u16b", "raw_s32l", "raw_s32b", "raw_u32l", "raw_u32b",
+                 "raw_f32l", "raw_f32b", "raw_f64l", "raw_f64b"]
+
+
+def iq_convert(mode: str, raw: bytes) -> np.ndarray:
+    """Raw capture bytes in one of the reference's reader modes -> complex64 samples (dabgpu_iq_convert, host only)."""
+    L = load_library()
+    buf = np.frombuffer(raw, dtype=np.uint8)
+    out = np.empty(buf.size + 2, dtype=np.float32)
+    n = C.c_size_t(0)
+    _check(L.dabgpu_iq_convert(mode.encode(), buf.ctypes.data if buf.size else None, buf.size, out.ctypes.data, out.size, C.byref(n)))
+    m = n.value - (n.value % 2)
+    return out[:m].view(np.complex64).copy()
+
+
+def softbits_to_bytes(bits: np.ndarray) -> np.ndarray:
+    L = load_library()
+    bits = np.ascontiguousarray(bits, dtype=np.int8)
+    out = np.empty(bits.size // 8, dtype=np.uint8)
+    _check(L.dabgpu_softbits_to_bytes(bits.ctypes.data, bits.size, out.ctypes.data))
+    return out
+
+
+def bytes_to_softbits(b: np.ndarray) -> np.ndarray:
+    L = load_library()
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    out = np.empty(b.size * 8, dtype=np.int8)
+    _check(L.dabgpu_bytes_to_softbits(b.ctypes.data, b.size, out.ctypes.data))
+    return out

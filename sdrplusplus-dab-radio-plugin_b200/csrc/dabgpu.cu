@@ -7,6 +7,7 @@
 #include "dabplus.cuh"
 #include "ofdm_host.cuh"
 #include "../host/fic_autoconfig.hpp"
+#include "../host/capture_formats.hpp"
 
 #define DABGPU_VERSION "dabgpu 0.1 (sm_100a)"
 
@@ -549,6 +550,32 @@ int dabgpu_softbits_push(dabgpu_ctx* ctx, const int8_t* frames_host, size_t stri
     }
     CUDA_TRY(cudaMemcpyAsync(ctx->d_frames_written.as<uint32_t>() + first, written, size_t(n) * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DABGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Capture file formats (host only)
+// ---------------------------------------------------------------------------------------------
+int dabgpu_iq_convert(const char* mode, const void* raw, size_t n_bytes, float* out_c32, size_t out_cap_floats, size_t* n_floats) {
+    if (!mode || (!raw && n_bytes) || !out_c32 || !n_floats) return set_error(DABGPU_ERR_INVALID, "null argument");
+    const int fmt = dabgpu_host::iq_format_from_mode(mode);
+    if (fmt < 0) return set_error(DABGPU_ERR_INVALID, "Unknown iq file format: '%s'", mode);
+    const size_t n = n_bytes / dabgpu_host::iq_component_bytes(fmt);
+    if (n > out_cap_floats) return set_error(DABGPU_ERR_OVERFLOW, "%zu components, room for %zu", n, out_cap_floats);
+    *n_floats = dabgpu_host::iq_convert_to_c32(fmt, static_cast<const uint8_t*>(raw), n_bytes, out_c32);
+    return DABGPU_OK;
+}
+
+int dabgpu_softbits_to_bytes(const int8_t* bits, size_t n_bits, uint8_t* bytes) {
+    if (!bits || !bytes) return set_error(DABGPU_ERR_INVALID, "null argument");
+    if (n_bits % 8) return set_error(DABGPU_ERR_INVALID, "%zu soft bits are not a whole number of bytes", n_bits);
+    dabgpu_host::softbits_to_hard_bytes(bits, n_bits / 8, bytes);
+    return DABGPU_OK;
+}
+
+int dabgpu_bytes_to_softbits(const uint8_t* bytes, size_t n_bytes, int8_t* bits) {
+    if (!bits || !bytes) return set_error(DABGPU_ERR_INVALID, "null argument");
+    dabgpu_host::hard_bytes_to_softbits(bytes, n_bytes, bits);
     return DABGPU_OK;
 }
 
