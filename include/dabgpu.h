@@ -73,6 +73,8 @@ typedef struct {
  * one trellis per warp (k_viterbi); both are bit-exact with the reference.  These flags pin one mapping (tests, profiling). */
 #define DABGPU_FLAG_VIT_LANES_ALWAYS 2u
 #define DABGPU_FLAG_VIT_LANES_NEVER 4u
+/* Keep the synchronisation responses of every stream on the device for the GUI taps (dabgpu_ofdm_get_response). */
+#define DABGPU_FLAG_DIAG_TAPS 8u
 
 DABGPU_API const char* dabgpu_version(void);
 DABGPU_API const char* dabgpu_last_error(void);
@@ -146,6 +148,11 @@ DABGPU_API int dabgpu_ofdm_advance(dabgpu_ctx* ctx, int first_stream, int n_stre
  * and fine time offset as observed when the frame was emitted. */
 typedef struct { float freq_coarse_offset, freq_fine_offset; int fine_time_offset; int frame_index; } dabgpu_frame_info;
 DABGPU_API int dabgpu_ofdm_get_status(dabgpu_ctx* ctx, int stream, dabgpu_ofdm_status* out);
+/* GUI taps served from device buffers (contexts created with DABGPU_FLAG_DIAG_TAPS): nb_fft floats in dB of the last
+ * synchronisation of the stream.  kind 0 = OFDM_Demod::GetImpulseResponse (fine time correlation, ofdm_demodulator.cpp:473-548),
+ * kind 1 = OFDM_Demod::GetCoarseFrequencyResponse (ofdm_demodulator.cpp:360-471), both read by the plugin's render code
+ * (src/render_radio_block.cpp:192-214).  GetFrameFFT / the NULL-symbol spectrum are not served yet. */
+DABGPU_API int dabgpu_ofdm_get_response(dabgpu_ctx* ctx, int stream, int kind, float* out, int n_floats);
 DABGPU_API int dabgpu_ofdm_pop_frames(dabgpu_ctx* ctx, int stream, int8_t* frames_host, int max_frames,
                                       dabgpu_frame_info* infos, int* n_frames_out);
 /* Bulk variant used by throughput harnesses: newest frame of every stream in [first, first+n) that

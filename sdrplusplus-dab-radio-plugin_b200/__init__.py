@@ -101,7 +101,7 @@ EXPORTS = [
     "dabgpu_get_counters", "dabgpu_submit", "dabgpu_wait", "dabgpu_msc_get_layout",
     "dabgpu_ofdm_set_config", "dabgpu_fic_decode", "dabgpu_dabplus_open", "dabgpu_dabplus_close", "dabgpu_dabplus_process",
     "dabgpu_autocfg_create", "dabgpu_autocfg_destroy", "dabgpu_autocfg_push_fibs", "dabgpu_autocfg_dump", "dabgpu_autocfg_runnable",
-    "dabgpu_autocfg_apply", "dabgpu_iq_convert", "dabgpu_softbits_to_bytes", "dabgpu_bytes_to_softbits",
+    "dabgpu_autocfg_apply", "dabgpu_ofdm_get_response", "dabgpu_iq_convert", "dabgpu_softbits_to_bytes", "dabgpu_bytes_to_softbits",
 ]
 
 _lib = None
@@ -163,6 +163,7 @@ def load_library() -> C.CDLL:
     L.dabgpu_autocfg_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.dabgpu_autocfg_runnable.argtypes = [C.c_void_p, C.POINTER(SubchannelC), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.dabgpu_autocfg_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.dabgpu_ofdm_get_response.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
     L.dabgpu_iq_convert.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.dabgpu_softbits_to_bytes.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     L.dabgpu_bytes_to_softbits.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
@@ -407,6 +408,12 @@ class DabGpu:
         st = OfdmStatus()
         _check(self.L.dabgpu_ofdm_get_status(self.h, stream, C.byref(st)))
         return {n: getattr(st, n) for n, _ in OfdmStatus._fields_}
+
+    def ofdm_response(self, stream: int, kind: int) -> np.ndarray:
+        """GUI tap: kind 0 = impulse response, 1 = coarse frequency response (dB, nb_fft floats); needs FLAG_DIAG_TAPS."""
+        out = np.empty(self.P.nb_fft, dtype=np.float32)
+        _check(self.L.dabgpu_ofdm_get_response(self.h, stream, kind, out.ctypes.data, out.size))
+        return out
 
     def ofdm_pop_frames(self, stream: int, max_frames: int = 64):
         frames = np.zeros((max_frames, self.P.nb_frame_bits), dtype=np.int8)

@@ -905,6 +905,19 @@ int dabgpu_ofdm_advance(dabgpu_ctx* ctx, int first, int n, int n_samples, int bl
     return ofdm_advance(ctx->ofdm, first, n, n_samples, block_size, ctx->stream);
 }
 
+int dabgpu_ofdm_get_response(dabgpu_ctx* ctx, int stream, int kind, float* out, int n_floats) {
+    int rc = check_stream_range(ctx, stream, 1);
+    if (rc) return rc;
+    if (!out || kind < 0 || kind > 1) return set_error(DABGPU_ERR_INVALID, "bad argument");
+    if (!ctx->ofdm.d_diag.p) return set_error(DABGPU_ERR_STATE, "context was created without DABGPU_FLAG_DIAG_TAPS");
+    if (n_floats < ctx->P.nb_fft) return set_error(DABGPU_ERR_OVERFLOW, "response needs %d floats", ctx->P.nb_fft);
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpy(out, ctx->ofdm.d_diag.as<float>() + (size_t(stream) * 2 + size_t(kind)) * size_t(ctx->P.nb_fft), size_t(ctx->P.nb_fft) * sizeof(float),
+                        cudaMemcpyDeviceToHost));
+    return DABGPU_OK;
+}
+
 int dabgpu_ofdm_get_status(dabgpu_ctx* ctx, int stream, dabgpu_ofdm_status* out) {
     int rc = check_stream_range(ctx, stream, 1);
     if (rc) return rc;

@@ -64,6 +64,7 @@ struct OfdmDev {
     float2* corr;        // [stream][Tnull+Tsym]
     float2* head;        // [stream][Tsym+CP]
     float* phase_err;    // [stream][L]
+    float* diag;         // optional (DABGPU_FLAG_DIAG_TAPS): [stream][2][N] = impulse response, coarse frequency response (dB)
     // tables
     const float2* tw;            // exp(-2*pi*i*n/N)
     const float2* prs_fft_conj;  // conj(PRS spectrum), natural order
@@ -455,6 +456,7 @@ k_ofdm_ctl(const OfdmDev D, const int first_stream, const int n_new_samples, con
                 const int i = tid + j * NT;
                 const int p = D.dpos[(i + N / 2) % N];
                 b_re[i] = 20.0f * log10f(sqrtf(a_re[p] * a_re[p] + a_im[p] * a_im[p]));
+                if (D.diag) D.diag[(size_t(s) * 2 + 1) * N + i] = b_re[i];   // OFDM_Demod::GetCoarseFrequencyResponse
             }
             __syncthreads();
             const int Mh = N / 2;
@@ -527,6 +529,7 @@ k_ofdm_ctl(const OfdmDev D, const int first_stream, const int n_new_samples, con
                 const int i = tid + j * NT;
                 const int p = D.dpos[i];
                 a_re[i] = 20.0f * log10f(sqrtf(b_re[p] * b_re[p] + b_im[p] * b_im[p]));
+                if (D.diag) D.diag[(size_t(s) * 2 + 0) * N + i] = a_re[i];   // OFDM_Demod::GetImpulseResponse
             }
             __syncthreads();
             const float decay = 1.0f - D.cfg.impulse_peak_distance_probability;

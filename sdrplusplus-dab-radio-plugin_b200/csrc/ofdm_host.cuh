@@ -16,7 +16,7 @@ struct OfdmState {
     size_t ring_cap = 0;          // internal ring capacity (samples)
     bool external_ring = false;
     int bps = 2;
-    DevBuf d_ring, d_st, d_null_ring, d_corr, d_head, d_phase, d_tw, d_prs_conj, d_prs_time, d_dpos, d_outpos, d_obin, d_stage, d_produced;
+    DevBuf d_diag, d_ring, d_st, d_null_ring, d_corr, d_head, d_phase, d_tw, d_prs_conj, d_prs_time, d_dpos, d_outpos, d_obin, d_stage, d_produced;
     int num_sms = 148;
     // second stream: the streams of a launch are split in two groups so that the latency-bound control kernel of one
     // group overlaps the demodulation kernel of the other
@@ -99,6 +99,10 @@ static int ofdm_init(OfdmState& O, const dabgpu_config& cfg, const dabgpu_params
     if ((rc = O.d_corr.alloc(size_t(S) * (P.nb_null_period + P.nb_symbol_period) * sizeof(float2)))) return rc;
     if ((rc = O.d_head.alloc(size_t(S) * (P.nb_symbol_period + P.nb_cyclic_prefix) * sizeof(float2)))) return rc;
     if ((rc = O.d_phase.alloc(size_t(S) * P.nb_frame_symbols * sizeof(float)))) return rc;
+    if (cfg.flags & DABGPU_FLAG_DIAG_TAPS) {
+        if ((rc = O.d_diag.alloc(size_t(S) * 2 * size_t(P.nb_fft) * sizeof(float)))) return rc;
+        cudaMemset(O.d_diag.p, 0, O.d_diag.bytes);
+    }
     if ((rc = O.d_produced.alloc(size_t(S)))) return rc;
     if ((rc = O.h_produced.alloc(size_t(S)))) return rc;
     cudaMemset(O.d_ring.p, 0, O.d_ring.bytes);
@@ -213,6 +217,7 @@ static int ofdm_init(OfdmState& O, const dabgpu_config& cfg, const dabgpu_params
     D.corr = O.d_corr.as<float2>();
     D.head = O.d_head.as<float2>();
     D.phase_err = O.d_phase.as<float>();
+    D.diag = O.d_diag.as<float>();   // null unless DABGPU_FLAG_DIAG_TAPS
     D.tw = O.d_tw.as<float2>();
     D.prs_fft_conj = O.d_prs_conj.as<float2>();
     D.prs_time_ref = O.d_prs_time.as<float2>();
@@ -239,7 +244,7 @@ static int ofdm_init(OfdmState& O, const dabgpu_config& cfg, const dabgpu_params
 }
 
 static void ofdm_destroy(OfdmState& O) {
-    DevBuf* bufs[] = {&O.d_ring, &O.d_st, &O.d_null_ring, &O.d_corr, &O.d_head, &O.d_phase, &O.d_tw, &O.d_prs_conj, &O.d_prs_time,
+    DevBuf* bufs[] = {&O.d_diag, &O.d_ring, &O.d_st, &O.d_null_ring, &O.d_corr, &O.d_head, &O.d_phase, &O.d_tw, &O.d_prs_conj, &O.d_prs_time,
                       &O.d_dpos, &O.d_outpos, &O.d_obin, &O.d_stage, &O.d_produced};
     for (DevBuf* b : bufs) b->release();
     if (O.aux_stream) { cudaStreamSynchronize(O.aux_stream); cudaStreamDestroy(O.aux_stream); O.aux_stream = nullptr; }

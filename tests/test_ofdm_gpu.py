@@ -210,3 +210,29 @@ def test_pipelined_submit_wait_equals_synchronous_process(gpu_ctx, tx, pyref):
     assert sum(int(e[1].sum()) for e in expected) >= S * (n_frames - 3)
     g_sync.close()
     g_pipe.close()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_gui_taps_match_reference(gpu_ctx, tx, pyref, ref_ok, mode):
+    """SURVEY section 8(f) rank 4 (partial): OFDM_Demod::GetImpulseResponse / GetCoarseFrequencyResponse served from device buffers.
+    The responses are float32 dB values behind different FFT implementations: the peak must sit at the same index and every bin
+    within 40 dB of the peak must agree to 0.05 dB."""
+    block = 65536
+    u8, _, _ = _recording(tx, mode, 4 if mode == 1 else 8, 18.0, 2.6e-3, 4321, seed=70 + mode)
+    ref = pyref.RefOfdm(mode, 1)
+    g = gpu_ctx.DabGpu(mode=mode, max_streams=1, flags=8)   # DABGPU_FLAG_DIAG_TAPS
+    plain = gpu_ctx.DabGpu(mode=mode, max_streams=1)
+    for off in range(0, u8.size // 2, block):
+        ref.process_u8(u8[2 * off:2 * (off + block)])
+        g.ofdm_process(u8[None, 2 * off:2 * (off + block)], block_size=block)
+    n = g.P.nb_fft
+    assert len(ref.pop_frames()) == len(g.ofdm_pop_frames(0)) > 0
+    for kind, exp in ((0, ref.impulse_response(n)), (1, ref.coarse_response(n))):
+        got = g.ofdm_response(0, kind)
+        assert int(np.argmax(got)) == int(np.argmax(exp)), kind
+        strong = exp > exp.max() - 40.0
+        assert strong.sum() > 0 and np.abs(got[strong] - exp[strong]).max() < 0.05, (kind, np.abs(got[strong] - exp[strong]).max())
+    with pytest.raises(gpu_ctx.DabGpuError):
+        plain.ofdm_response(0, 0)        # taps are opt-in: the context was created without the flag
+    g.close()
+    plain.close()
