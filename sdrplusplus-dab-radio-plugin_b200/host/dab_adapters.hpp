@@ -30,6 +30,7 @@
 #include <string>
 #include <vector>
 #include "../../include/dabgpu.h"
+#include "fic_autoconfig.hpp"
 
 namespace dabgpu_host {
 
@@ -571,13 +572,50 @@ private:
     std::mutex m_mutex_data;
     std::vector<std::unique_ptr<Channel>> m_channels;
     Observable<span<const uint8_t>> m_obs_on_fib;
+    Observable<subchannel_id_t, Channel&> m_obs_audio_channel;
     std::vector<uint8_t> m_fibs, m_crc, m_msc, m_log;
+    FIC_Autoconfig m_autocfg;
+    bool m_self_configure = false;
+    std::vector<uint8_t> m_configured_ids;
+    // BasicRadio::UpdateAfterProcessing (basic_radio.cpp:83-154): new complete audio sub-channels get a decoder and observers
+    // are told.  The GPU context is reconfigured as a whole, so every de-interleaver restarts when the set grows.
+    void update_after_processing() {
+        std::vector<dabgpu_subchannel> subs;
+        std::vector<uint8_t> ids;
+        m_autocfg.Runnable(subs, ids);
+        if (ids == m_configured_ids) return;
+        if (!m_ctx->check(dabgpu_msc_configure(m_ctx->get(), 0, subs.data(), int(subs.size())))) return;
+        std::vector<std::unique_ptr<Channel>> channels;
+        for (size_t i = 0; i < subs.size(); i++) {
+            auto ch = std::make_unique<Channel>();
+            ch->subchannel.id = ids[i];
+            ch->subchannel.start_address = uint16_t(subs[i].start_address);
+            ch->subchannel.length = uint16_t(subs[i].length);
+            ch->subchannel.is_uep = subs[i].is_uep != 0;
+            ch->subchannel.uep_prot_index = uint8_t(subs[i].uep_prot_index);
+            ch->subchannel.eep_prot_level = uint8_t(subs[i].eep_prot_level);
+            ch->subchannel.eep_type = subs[i].eep_type_b ? EEP_Type::TYPE_B : EEP_Type::TYPE_A;
+            ch->is_dabplus = subs[i].is_dabplus != 0;
+            channels.push_back(std::move(ch));
+        }
+        const std::vector<uint8_t> known = m_configured_ids;
+        m_channels = std::move(channels);
+        m_configured_ids = ids;
+        for (size_t i = 0; i < ids.size(); i++) {
+            bool is_new = true;
+            for (uint8_t k : known) is_new = is_new && (k != ids[i]);
+            if (is_new) m_obs_audio_channel.Notify(ids[i], *m_channels[i]);
+        }
+    }
     void deliver() {
         dabgpu_chan_status st;
         if (!m_ctx->check(dabgpu_chan_get_status(m_ctx->get(), 0, &st)) || !st.decoded) return;
         if (!m_ctx->check(dabgpu_chan_get_fic(m_ctx->get(), 0, m_fibs.data(), m_crc.data()))) return;
         for (int i = 0; i < m_params.nb_fibs; i++)
-            if (m_crc[size_t(i)]) m_obs_on_fib.Notify(span<const uint8_t>(m_fibs.data() + 32 * size_t(i), 30));
+            if (m_crc[size_t(i)]) {
+                m_obs_on_fib.Notify(span<const uint8_t>(m_fibs.data() + 32 * size_t(i), 30));
+                if (m_self_configure) m_autocfg.ProcessFIB(m_fibs.data() + 32 * size_t(i), 30);
+            }
         for (size_t k = 0; k < m_channels.size(); k++) {
             Channel& ch = *m_channels[k];
             uint8_t valid[8] = {0};
@@ -590,6 +628,7 @@ private:
                 if (m_ctx->check(dabgpu_chan_get_dabplus_events(m_ctx->get(), 0, int(k), m_log.data(), m_log.size(), &n))) ch.dabplus.dispatch(m_log.data(), n);
             }
         }
+        if (m_self_configure) update_after_processing();
     }
 public:
     explicit BasicRadio(const DAB_Parameters& params, const size_t nb_threads = 0, std::shared_ptr<Context> ctx = nullptr)
@@ -633,6 +672,11 @@ public:
             deliver();
         }
     }
+    // Let the FIC decide: FIG 0/1 + 0/2 (+ 0/3, 0/14) are parsed on the host (fic_autoconfig.hpp) and the sub-channel set is
+    // applied after the frame that completed it, like the reference's BasicRadio does without being asked.
+    void EnableSelfConfiguration(bool on = true) { m_self_configure = on; }
+    auto& On_Audio_Channel() { return m_obs_audio_channel; }
+    const FIC_Autoconfig& GetFICDatabase() const { return m_autocfg; }
     Channel* Get_Channel(size_t index) { return index < m_channels.size() ? m_channels[index].get() : nullptr; }
     size_t GetTotalChannels() const { return m_channels.size(); }
     auto& GetMutex() { return m_mutex_data; }

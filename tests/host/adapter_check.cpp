@@ -188,8 +188,30 @@ static void run_radio(Reader& in, Writer& out) {
     out.f32(demod->GetNetFrequencyOffset());
 }
 
+// mode, n_frames, frame_bits, soft-bit frames.  BasicRadio configures itself from the FIC (EnableSelfConfiguration).
+// Output records: {4, id, start, length, is_uep, uep_index, eep_level, eep_type_b, is_dabplus, frame} when a channel is announced,
+// {3, id, n, bytes} per decoded logical frame, {0, n_channels} at the end.
+static void run_selfcfg(Reader& in, Writer& out) {
+    const int mode = in.i32(), n_frames = in.i32(), frame_bits = in.i32();
+    BasicRadio radio(get_dab_parameters(mode), 1);
+    radio.EnableSelfConfiguration();
+    int frame = 0;
+    radio.On_Audio_Channel().Attach([&](subchannel_id_t id, BasicRadio::Channel& ch) {
+        const Subchannel& s = ch.subchannel;
+        out.i32(4); out.i32(id); out.i32(s.start_address); out.i32(s.length); out.i32(s.is_uep); out.i32(s.uep_prot_index); out.i32(s.eep_prot_level);
+        out.i32(s.eep_type == EEP_Type::TYPE_B); out.i32(ch.is_dabplus); out.i32(frame);
+        ch.on_msc_data.Attach([&out, id](span<const uint8_t> b) { out.i32(3); out.i32(id); out.i32(int32_t(b.size())); out.bytes(b.data(), b.size()); });
+    });
+    for (frame = 0; frame < n_frames; frame++) {
+        const int8_t* f = reinterpret_cast<const int8_t*>(in.bytes(size_t(frame_bits)));
+        radio.Process(span<const viterbi_bit_t>(f, size_t(frame_bits)));
+    }
+    out.i32(0);
+    out.i32(int32_t(radio.GetTotalChannels()));
+}
+
 int main(int argc, char** argv) {
-    if (argc != 4) { std::cerr << "usage: adapter_check <viterbi|fic|msc|rs|aac|radio> in.bin out.bin\n"; return 1; }
+    if (argc != 4) { std::cerr << "usage: adapter_check <viterbi|fic|msc|rs|aac|radio|selfcfg> in.bin out.bin\n"; return 1; }
     try {
         Reader in(argv[2]);
         Writer out;
@@ -200,6 +222,7 @@ int main(int argc, char** argv) {
         else if (what == "rs") run_rs(in, out);
         else if (what == "aac") run_aac(in, out);
         else if (what == "radio") run_radio(in, out);
+        else if (what == "selfcfg") run_selfcfg(in, out);
         else { std::cerr << "unknown test " << what << "\n"; return 1; }
         out.save(argv[3]);
     } catch (const std::exception& e) {

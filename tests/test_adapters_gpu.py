@@ -260,3 +260,46 @@ def test_radio_block_chain(driver, tx, pyref):
         assert len(msc[k]) == len(exp_msc[k])
         for a, b in zip(msc[k], exp_msc[k]):
             assert np.array_equal(a, b)
+
+
+def test_basic_radio_configures_itself_from_the_fic(driver, tx, pyref):
+    """BasicRadio with EnableSelfConfiguration(): soft-bit frames in, channels announced through On_Audio_Channel as the FIC
+    completes them (FIG 0/1 + 0/2), then their bytes equal the oracle's MSC decoders started at the same frame."""
+    rng = np.random.default_rng(8)
+    subs = [tx.Subchannel(5, 0, 48, eep_level=2), tx.Subchannel(11, 48, 54, eep_level=2, eep_type_b=True, dabplus=False),
+            tx.Subchannel(20, 102, 35, is_uep=True, uep_index=4, dabplus=False)]
+    ens = tx.EnsembleTx(1, subs, seed=31)
+    n_frames = 9
+    frames = [tx.hard_to_soft(ens.next_frame_bits(), rng, snr_db=7.0) for _ in range(n_frames)]
+    out = _run(driver, "selfcfg", _i32(1, n_frames, frames[0].size) + b"".join(f.tobytes() for f in frames))
+    announced, data, off = [], {}, 0
+    while True:
+        tag, = struct.unpack_from("<i", out, off)
+        off += 4
+        if tag == 0:
+            n_channels, = struct.unpack_from("<i", out, off)
+            break
+        if tag == 4:
+            announced.append(struct.unpack_from("<9i", out, off))
+            off += 36
+        else:
+            sid, ln = struct.unpack_from("<2i", out, off)
+            data.setdefault(sid, []).append(np.frombuffer(out, dtype=np.uint8, count=ln, offset=off + 8))
+            off += 8 + ln
+    assert n_channels == len(subs)
+    assert [a[0] for a in announced] == [s.id for s in subs]
+    for a, s in zip(announced, subs):
+        assert a[1:4] == (s.start_address, s.length, int(s.is_uep)) and a[7] == int(s.dabplus) and a[8] == 0   # all known after the first frame
+        assert (a[4] == s.uep_index) if s.is_uep else (a[5:7] == (s.eep_level, int(s.eep_type_b)))
+    mk = pyref.RefMsc if pyref.ref_available() else pyref.PortMsc
+    for s in subs:
+        o = mk(s.start_address, s.length, s.is_uep, s.uep_index, s.eep_level, s.eep_type_b)
+        exp = []
+        for f in frames[1:]:                      # the decoder exists from the frame after the one that configured it
+            for c in range(4):
+                e = o.decode_cif(f[9216 + c * 55296: 9216 + (c + 1) * 55296])
+                if e.size:
+                    exp.append(e)
+        got = data.get(s.id, [])
+        assert len(got) == len(exp) > 0, s.id
+        assert all(np.array_equal(g, e) for g, e in zip(got, exp)), s.id
