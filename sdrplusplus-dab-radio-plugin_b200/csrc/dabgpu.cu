@@ -372,7 +372,7 @@ static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, 
         k_vit_count<<<nb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, plan);
         k_vit_plan<<<1, 32, 0, ctx->stream>>>(plan, ctx->vl_mode, ctx->vl_min_jobs, rows, groups);
         k_vit_scatter<<<nb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, plan, ctx->d_vllist.as<uint32_t>());
-        k_vit_prep<<<groups, 128, 0, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(), ctx->d_vlsym.as<uint32_t>(), ctx->chan.geom);
+        k_vit_prep<<<groups, VP_WARPS * 32, 0, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(), ctx->d_vlsym.as<uint32_t>(), ctx->chan.geom);
         ctx->prof.end(ctx->stream);
         ctx->prof.begin(PROF_VITERBI, ctx->stream);
         if (!lanes_wide) {

@@ -97,46 +97,106 @@ __device__ __forceinline__ void vl_locate(const VlPlan* __restrict__ plan, const
     row0 = plan->row_base[b] + gi * vl_bucket_rows(b);
 }
 
-// One CTA (4 warps) per group; warp w fills the columns 8w..8w+7 of the group's symbol matrix, lane = trellis step within
-// a chunk of 32, so that every store is a full 32-byte sector.
-__global__ void __launch_bounds__(128)
+// Per-trellis puncturing state of k_vit_prep: the segment that contains the first step of the current 32-step chunk, with its
+// tables, so that the common case (the whole chunk inside one segment) costs a dozen instructions per step instead of the
+// segment search and table lookups of vit_load_step.
+struct PrepSeg { uint32_t seg, seg_end, start, inb, cntw, K, pref_lo, pref_hi; };
+__device__ __forceinline__ void prep_seg_load(PrepSeg& S, const VitJobDev& J, const uint32_t seg) {
+    const uint32_t pi = J.seg_pi[seg];
+    S.seg = seg;
+    S.seg_end = J.seg_step_end[seg];
+    S.start = seg ? J.seg_step_end[seg - 1u] : 0u;
+    S.inb = J.seg_in_base[seg];
+    S.cntw = c_pi_cnt[pi];
+    S.K = c_pi_K[pi];
+    S.pref_lo = uint32_t(c_pi_pref[pi]);
+    S.pref_hi = uint32_t(c_pi_pref[pi] >> 32);
+}
+
+// One CTA per group; warp w fills the columns VP_JPW*w .. VP_JPW*w + VP_JPW-1 of the group's symbol matrix, lane = trellis
+// step within a chunk of 32.  The pass is a chain of dependent L2 round trips per warp (one per trellis and chunk: the byte
+// loads of a step are predicated on the puncturing count), so its time is (trellises per warp) x (chunks) x latency: two
+// trellises per warp and 16 warps per CTA instead of eight and four cut that chain by four.
+#define VP_JPW 2u
+#define VP_WARPS (32u / VP_JPW)
+__global__ void __launch_bounds__(VP_WARPS * 32)
 k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, const uint32_t* __restrict__ list, uint32_t* __restrict__ sym, const GatherGeom G) {
     __shared__ VitJobDev sJ[32];
     __shared__ uint32_t s_rowoff[32][16];
+    __shared__ PrepSeg sSeg[32];
     const uint32_t g = blockIdx.x;
     if (g >= plan->n_groups) return;
     uint32_t list0, n_in, row0;
     vl_locate(plan, g, list0, n_in, row0);
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     if (threadIdx.x < 32u) {
-        if (threadIdx.x < n_in) sJ[threadIdx.x] = jobs[list[list0 + threadIdx.x]];
-        else sJ[threadIdx.x].total_steps = 0u;
+        if (threadIdx.x < n_in) {
+            sJ[threadIdx.x] = jobs[list[list0 + threadIdx.x]];
+            uint32_t seg = 0;
+            while (seg < DABGPU_MAX_SEGMENTS - 1u && sJ[threadIdx.x].seg_step_end[seg] == 0u) seg++;   // skip empty leading segments
+            prep_seg_load(sSeg[threadIdx.x], sJ[threadIdx.x], seg);
+        } else {
+            sJ[threadIdx.x].total_steps = 0u;
+            sSeg[threadIdx.x].seg_end = 0u;   // never on the fast path
+        }
     }
     __syncthreads();
     uint32_t steps_g = sJ[lane].total_steps;
     steps_g = __reduce_max_sync(FULL_MASK, steps_g);
     const uint32_t padded = ((steps_g + VL_UNROLL - 1u) / VL_UNROLL) * VL_UNROLL + VL_UNROLL;
 #pragma unroll 1
-    for (uint32_t jj = 0; jj < 8u; jj++) {
-        const uint32_t q = 8u * w + jj;
+    for (uint32_t jj = 0; jj < VP_JPW; jj++) {
+        const uint32_t q = VP_JPW * w + jj;
         if (sJ[q].total_steps != 0u) vit_fill_rowoff(sJ[q], G, s_rowoff[q], lane);
     }
     __syncwarp();
-    uint32_t* dst = sym + (size_t(row0) * 32u + 8u * w);
+    uint32_t* dst = sym + (size_t(row0) * 32u + VP_JPW * w);
+    // Measured alternatives: a planar soft-bit layout (positions r mod 16 contiguous per CIF) removed
+    // the DRAM over-fetch of this pass (274 -> 70 MB) but not its time, and cost k_ofdm_demod 2 percent; issuing the byte loads
+    // of the 8 trellises round by round (8 in flight per lane) did not help either: the pass is bound by its instruction count
+    // (about 100 per trellis step and lane with vit_load_step), hence the cached segment state below.
 #pragma unroll 1
     for (uint32_t t0 = 0; t0 < padded; t0 += 32u) {
         const uint32_t t = t0 + lane;
-        uint32_t v[8];
+        uint32_t v[VP_JPW];
 #pragma unroll
-        for (uint32_t jj = 0; jj < 8u; jj++) {
-            const uint32_t q = 8u * w + jj;
-            v[jj] = (t < sJ[q].total_steps) ? vit_load_step(sJ[q], s_rowoff[q], t) : 0u;
+        for (uint32_t jj = 0; jj < VP_JPW; jj++) {
+            const uint32_t q = VP_JPW * w + jj;
+            const PrepSeg& S = sSeg[q];
+            if (t0 + 32u <= S.seg_end) {
+                // the whole chunk lies inside the cached segment (warp-uniform test): DAB_Viterbi_Decoder::depuncture_symbols
+                // (dab_viterbi_decoder.cpp:131-181) with segment, code and tables read once per warp
+                const uint32_t u = t - S.start, g8 = u & 7u;
+                const uint32_t cnt = (S.cntw >> (4u * g8)) & 0xFu;
+                const uint32_t pre = (((g8 & 4u) ? S.pref_hi : S.pref_lo) >> (8u * (g8 & 3u))) & 0xFFu;
+                const uint32_t base = S.inb + (u >> 3) * S.K + pre;
+                const int8_t* __restrict__ src = sJ[q].src;
+                uint32_t word = 0;
+#pragma unroll
+                for (uint32_t r = 0; r < 4; r++) {
+                    if (r < cnt) {
+                        const uint32_t idx = base + r;
+                        word |= uint32_t(uint8_t(__ldg(src + (size_t(s_rowoff[q][idx & 15u]) + idx)))) << (8u * r);
+                    }
+                }
+                v[jj] = word;
+            } else {
+                v[jj] = (t < sJ[q].total_steps) ? vit_load_step(sJ[q], s_rowoff[q], t) : 0u;
+            }
         }
-        if (t < padded) {
-            uint4* p = reinterpret_cast<uint4*>(dst + size_t(t) * 32u);
-            p[0] = make_uint4(v[0], v[1], v[2], v[3]);
-            p[1] = make_uint4(v[4], v[5], v[6], v[7]);
+        if (t < padded) *reinterpret_cast<uint2*>(dst + size_t(t) * 32u) = make_uint2(v[0], v[1]);
+        // move the cached segments to the one that contains the first step of the next chunk
+        __syncwarp();
+        if (lane < VP_JPW) {
+            const uint32_t q = VP_JPW * w + lane;
+            PrepSeg& S = sSeg[q];
+            if (S.seg_end != 0u && t0 + 32u >= S.seg_end && S.seg < DABGPU_MAX_SEGMENTS - 1u) {
+                uint32_t seg = S.seg;
+                while (seg < DABGPU_MAX_SEGMENTS - 1u && t0 + 32u >= sJ[q].seg_step_end[seg]) seg++;
+                prep_seg_load(S, sJ[q], seg);
+            }
         }
+        __syncwarp();
     }
 }
 
