@@ -7,6 +7,7 @@
 //   CIF_Deinterleaver                    dab/msc/cif_deinterleaver.cpp:20-71  (fused into the Viterbi loader as a gather)
 #pragma once
 #include "viterbi.cuh"
+#include "viterbi_lanes.cuh"
 
 #define CIF_OUT_STRIDE 6912u     // decoded bytes per CIF can never exceed 55296/8
 #define FIC_GROUP_BYTES 128u     // 96 used in modes I/II/IV
@@ -46,7 +47,9 @@ enum { CNT_FRAMES_DEMOD = 0, CNT_FRAMES_CHAN, CNT_FIB_OK, CNT_FIB_TOTAL, CNT_MSC
        CNT_SF_FIRE_FAIL, CNT_AU_OK, CNT_AU_CRC_FAIL, CNT_COUNT };
 
 // One thread per potential job: (stream, j).  j < nb_cifs => FIB group j; otherwise sub-channel x CIF.
-__global__ void k_chan_build_jobs(const ChanDev C, VitJobDev* __restrict__ jobs, const int first_stream, const int n_streams) {
+// count_plan (optional): the histogram of trellis lengths that k_vit_plan needs is taken here, where the lengths are at hand,
+// instead of by a separate pass over the job array (k_vit_count).
+__global__ void k_chan_build_jobs(const ChanDev C, VitJobDev* __restrict__ jobs, const int first_stream, const int n_streams, VlPlan* __restrict__ count_plan) {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = uint32_t(n_streams) * C.jobs_per_stream;
     if (gid >= total) return;
@@ -102,30 +105,40 @@ __global__ void k_chan_build_jobs(const ChanDev C, VitJobDev* __restrict__ jobs,
         }
     }
     jobs[gid] = J;
+    if (count_plan != nullptr && J.total_steps != 0u) {
+        if (J.total_steps >= VL_MAX_STEPS) count_plan->oversize = 1u;
+        else atomicAdd(&count_plan->count[vl_bucket(J.total_steps)], 1u);
+    }
 }
 
-// One thread per stream: advance the consumption counters after the Viterbi pass.
-__global__ void k_chan_finish(const ChanDev C, const int first_stream, const int n_streams) {
-    const uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per stream: advance the consumption counters after the Viterbi pass (lanes over the sub-channels).
+__global__ void __launch_bounds__(32) k_chan_finish(const ChanDev C, const int first_stream, const int n_streams) {
+    const uint32_t si = blockIdx.x, lane = threadIdx.x;
     if (si >= uint32_t(n_streams)) return;
     const uint32_t s = uint32_t(first_stream) + si;
     if (!C.status[2 * s]) return;
     const uint32_t nb_cifs = C.geom.nb_cifs;
-    unsigned long long fib_ok = 0, bytes = 0;
-    if (C.fic_enabled) {
-        for (uint32_t c = 0; c < nb_cifs; c++)
-            for (uint32_t f = 0; f < C.nb_fibs_per_cif; f++) fib_ok += C.fic_crc[(size_t(s) * nb_cifs + c) * 4u + f];
-        atomicAdd(&C.counters[CNT_FIB_TOTAL], (unsigned long long)(nb_cifs * C.nb_fibs_per_cif));
-        atomicAdd(&C.counters[CNT_FIB_OK], fib_ok);
-    }
+    unsigned long long bytes = 0;
     const uint32_t ns = C.n_subs[s];
-    for (uint32_t sub = 0; sub < ns; sub++) {
+    for (uint32_t sub = lane; sub < ns; sub += 32u) {
         uint32_t& cc = C.cifs_consumed[size_t(s) * C.max_subs + sub];
+        const uint32_t nb = C.subcfg[size_t(s) * C.max_subs + sub].n_out_bytes;
         for (uint32_t c = 0; c < nb_cifs; c++)
-            if (C.msc_valid[(size_t(s) * nb_cifs + c) * C.max_subs + sub]) bytes += C.subcfg[size_t(s) * C.max_subs + sub].n_out_bytes;
+            if (C.msc_valid[(size_t(s) * nb_cifs + c) * C.max_subs + sub]) bytes += nb;
         cc = min(cc + nb_cifs, 1u << 30);
     }
-    atomicAdd(&C.counters[CNT_MSC_BYTES], bytes);
-    atomicAdd(&C.counters[CNT_FRAMES_CHAN], 1ull);
-    C.frames_decoded[s] += 1u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(FULL_MASK, bytes, o);
+    if (lane == 0) {
+        if (C.fic_enabled) {
+            unsigned long long fib_ok = 0;
+            for (uint32_t c = 0; c < nb_cifs; c++)
+                for (uint32_t f = 0; f < C.nb_fibs_per_cif; f++) fib_ok += C.fic_crc[(size_t(s) * nb_cifs + c) * 4u + f];
+            atomicAdd(&C.counters[CNT_FIB_TOTAL], (unsigned long long)(nb_cifs * C.nb_fibs_per_cif));
+            atomicAdd(&C.counters[CNT_FIB_OK], fib_ok);
+        }
+        atomicAdd(&C.counters[CNT_MSC_BYTES], bytes);
+        atomicAdd(&C.counters[CNT_FRAMES_CHAN], 1ull);
+        C.frames_decoded[s] += 1u;
+    }
 }

@@ -336,7 +336,7 @@ struct VlBound {
     }
 };
 
-static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, const VlBound* bound) {
+static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, const VlBound* bound, bool precounted = false) {
     CUDA_TRY(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
     VlPlan* plan = nullptr;
     uint32_t rows = 0, groups = 0, active = 0;
@@ -367,9 +367,11 @@ static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, 
         static const VlConst kc = {0xFFFFFFFFu, 2u, 4u, 16u, 256u, 0x10000u};
         // planning + time de-interleave / de-puncture pass are accounted as "chan_misc", the decoders as "viterbi"
         ctx->prof.begin(PROF_CHAN_MISC, ctx->stream);
-        CUDA_TRY(cudaMemsetAsync(plan, 0, sizeof(VlPlan), ctx->stream));
         const int tb = 256, nb = (n_jobs + tb - 1) / tb;
-        k_vit_count<<<nb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, plan);
+        if (!precounted) {   // dabgpu_chan_decode takes the histogram while it builds the jobs
+            CUDA_TRY(cudaMemsetAsync(plan, 0, sizeof(VlPlan), ctx->stream));
+            k_vit_count<<<nb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, plan);
+        }
         k_vit_plan<<<1, 32, 0, ctx->stream>>>(plan, ctx->vl_mode, ctx->vl_min_jobs, rows, groups);
         k_vit_scatter<<<nb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, plan, ctx->d_vllist.as<uint32_t>());
         k_vit_prep<<<groups, VP_WARPS * 32, 0, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(), ctx->d_vlsym.as<uint32_t>(), ctx->chan.geom);
@@ -384,7 +386,7 @@ static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, 
                                                                                                 ctx->d_vlscratch.as<uint2>(), ctx->vl_scratch_rows,
                                                                                                 ctx->d_prbs.as<uint32_t>(), kc);
         }
-        ctx->launches += 5;
+        ctx->launches += precounted ? 4 : 5;
     } else {
         ctx->prof.begin(PROF_VITERBI, ctx->stream);
     }
@@ -657,8 +659,10 @@ int dabgpu_chan_decode(dabgpu_ctx* ctx, int first, int n) {
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     const uint32_t total = uint32_t(n) * ctx->chan.jobs_per_stream;
     if ((rc = ctx->d_jobs.alloc(size_t(total) * sizeof(VitJobDev)))) return rc;
+    VlPlan* count_plan = (ctx->vl_mode != 2) ? ctx->d_vlplan.as<VlPlan>() : nullptr;
     ctx->prof.begin(PROF_CHAN_MISC, ctx->stream);
-    k_chan_build_jobs<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->chan, ctx->d_jobs.as<VitJobDev>(), first, n);
+    if (count_plan) CUDA_TRY(cudaMemsetAsync(count_plan, 0, sizeof(VlPlan), ctx->stream));
+    k_chan_build_jobs<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->chan, ctx->d_jobs.as<VitJobDev>(), first, n, count_plan);
     ctx->prof.end(ctx->stream);
     ctx->launches++;
     if (ctx->vl_cache.first != first || ctx->vl_cache.n != n || ctx->vl_cache.epoch != ctx->cfg_epoch) {
@@ -675,11 +679,11 @@ int dabgpu_chan_decode(dabgpu_ctx* ctx, int first, int n) {
         VlBound vb;
         memcpy(vb.count, ctx->vl_cache.count, sizeof(vb.count));
         vb.max_steps = ctx->vl_cache.max_steps;
-        if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), int(total), &vb))) return rc;
+        if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), int(total), &vb, count_plan != nullptr))) return rc;
     }
     if ((rc = dabplus_run(ctx->dabplus, ctx->chan, first, n, ctx->stream, &ctx->launches, ctx->prof))) return rc;
     ctx->prof.begin(PROF_CHAN_MISC, ctx->stream);
-    k_chan_finish<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->chan, first, n);
+    k_chan_finish<<<n, 32, 0, ctx->stream>>>(ctx->chan, first, n);
     ctx->prof.end(ctx->stream);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
