@@ -151,8 +151,12 @@ DABGPU_API int dabgpu_ofdm_get_status(dabgpu_ctx* ctx, int stream, dabgpu_ofdm_s
 /* GUI taps served from device buffers (contexts created with DABGPU_FLAG_DIAG_TAPS): nb_fft floats in dB of the last
  * synchronisation of the stream.  kind 0 = OFDM_Demod::GetImpulseResponse (fine time correlation, ofdm_demodulator.cpp:473-548),
  * kind 1 = OFDM_Demod::GetCoarseFrequencyResponse (ofdm_demodulator.cpp:360-471), both read by the plugin's render code
- * (src/render_radio_block.cpp:192-214).  GetFrameFFT / the NULL-symbol spectrum are not served yet. */
+ * (src/render_radio_block.cpp:192-214). */
 DABGPU_API int dabgpu_ofdm_get_response(dabgpu_ctx* ctx, int stream, int kind, float* out, int n_floats);
+/* OFDM_Demod::GetFrameFFT (ofdm_demodulator.h:135): nb_frame_symbols x nb_fft complex<float> spectra (PRS first, natural bin
+ * order) of the last frame the stream emitted, recomputed on demand from the IQ still in the device ring.  The NULL-symbol row
+ * the reference appends is not served.  DABGPU_ERR_STATE until a frame that lies contiguously in the ring has been emitted. */
+DABGPU_API int dabgpu_ofdm_get_frame_fft(dabgpu_ctx* ctx, int stream, float* out, size_t n_floats);
 DABGPU_API int dabgpu_ofdm_pop_frames(dabgpu_ctx* ctx, int stream, int8_t* frames_host, int max_frames,
                                       dabgpu_frame_info* infos, int* n_frames_out);
 /* Bulk variant used by throughput harnesses: newest frame of every stream in [first, first+n) that

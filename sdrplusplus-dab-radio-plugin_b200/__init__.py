@@ -101,7 +101,7 @@ EXPORTS = [
     "dabgpu_get_counters", "dabgpu_submit", "dabgpu_wait", "dabgpu_msc_get_layout",
     "dabgpu_ofdm_set_config", "dabgpu_fic_decode", "dabgpu_dabplus_open", "dabgpu_dabplus_close", "dabgpu_dabplus_process",
     "dabgpu_autocfg_create", "dabgpu_autocfg_destroy", "dabgpu_autocfg_push_fibs", "dabgpu_autocfg_dump", "dabgpu_autocfg_runnable",
-    "dabgpu_autocfg_apply", "dabgpu_ofdm_get_response", "dabgpu_iq_convert", "dabgpu_softbits_to_bytes", "dabgpu_bytes_to_softbits",
+    "dabgpu_autocfg_apply", "dabgpu_ofdm_get_response", "dabgpu_ofdm_get_frame_fft", "dabgpu_iq_convert", "dabgpu_softbits_to_bytes", "dabgpu_bytes_to_softbits",
 ]
 
 _lib = None
@@ -164,6 +164,7 @@ def load_library() -> C.CDLL:
     L.dabgpu_autocfg_runnable.argtypes = [C.c_void_p, C.POINTER(SubchannelC), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.dabgpu_autocfg_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.dabgpu_ofdm_get_response.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.dabgpu_ofdm_get_frame_fft.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.dabgpu_iq_convert.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.dabgpu_softbits_to_bytes.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     L.dabgpu_bytes_to_softbits.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
@@ -413,6 +414,12 @@ class DabGpu:
         """GUI tap: kind 0 = impulse response, 1 = coarse frequency response (dB, nb_fft floats); needs FLAG_DIAG_TAPS."""
         out = np.empty(self.P.nb_fft, dtype=np.float32)
         _check(self.L.dabgpu_ofdm_get_response(self.h, stream, kind, out.ctypes.data, out.size))
+        return out
+
+    def ofdm_frame_fft(self, stream: int) -> np.ndarray:
+        """GUI tap: (nb_frame_symbols, nb_fft) complex64 spectra of the last emitted frame; needs FLAG_DIAG_TAPS."""
+        out = np.empty((self.P.nb_frame_symbols, self.P.nb_fft), dtype=np.complex64)
+        _check(self.L.dabgpu_ofdm_get_frame_fft(self.h, stream, out.ctypes.data, out.size * 2))
         return out
 
     def ofdm_pop_frames(self, stream: int, max_frames: int = 64):

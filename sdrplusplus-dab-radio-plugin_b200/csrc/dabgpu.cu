@@ -922,6 +922,16 @@ int dabgpu_ofdm_get_response(dabgpu_ctx* ctx, int stream, int kind, float* out, 
     return DABGPU_OK;
 }
 
+int dabgpu_ofdm_get_frame_fft(dabgpu_ctx* ctx, int stream, float* out, size_t n_floats) {
+    int rc = check_stream_range(ctx, stream, 1);
+    if (rc) return rc;
+    if (!out) return set_error(DABGPU_ERR_INVALID, "null output");
+    const size_t need = size_t(ctx->P.nb_frame_symbols) * size_t(ctx->P.nb_fft) * 2;
+    if (n_floats < need) return set_error(DABGPU_ERR_OVERFLOW, "frame spectrum needs %zu floats", need);
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    return ofdm_frame_fft(ctx->ofdm, stream, out, ctx->stream);
+}
+
 int dabgpu_ofdm_get_status(dabgpu_ctx* ctx, int stream, dabgpu_ofdm_status* out) {
     int rc = check_stream_range(ctx, stream, 1);
     if (rc) return rc;

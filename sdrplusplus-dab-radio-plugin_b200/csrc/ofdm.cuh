@@ -46,6 +46,9 @@ struct OfdmStream {
     unsigned long long consumed, push_end, block_end, frame_ring_base;
 };
 
+// Position and frequency of the last frame handed to the observers, kept for the on-demand GetFrameFFT tap.
+struct OfdmDiagMeta { unsigned long long abs0; float f; int32_t valid; };
+
 struct OfdmGeom {
     int L, Tsym, Tnull, CP, N, K, frame_bits, frame_samples, sym_per_chunk, n_chunks;
 };
@@ -65,6 +68,7 @@ struct OfdmDev {
     float2* head;        // [stream][Tsym+CP]
     float* phase_err;    // [stream][L]
     float* diag;         // optional (DABGPU_FLAG_DIAG_TAPS): [stream][2][N] = impulse response, coarse frequency response (dB)
+    struct OfdmDiagMeta* diag_meta;   // optional: where the last emitted frame of every stream sits in the IQ ring
     // tables
     const float2* tw;            // exp(-2*pi*i*n/N)
     const float2* prs_fft_conj;  // conj(PRS spectrum), natural order
@@ -316,6 +320,11 @@ k_ofdm_ctl(const OfdmDev D, const int first_stream, const int n_new_samples, con
             fi.freq_coarse_offset = st.coarse; fi.freq_fine_offset = st.fine; fi.fine_time_offset = st.fine_time_offset; fi.frame_index = int(w);
             D.frame_info[size_t(s) * (D.slot_mask + 1u) + (w & D.slot_mask)] = fi;
             D.frames_written[s] = w + 1u;
+            if (D.diag_meta) {
+                OfdmDiagMeta m;
+                m.abs0 = st.frame_ring_base - st.n_head; m.f = st.frame_f; m.valid = st.head_contig ? 1 : 0;
+                D.diag_meta[s] = m;
+            }
             st.produced_last++;
             st.pending = 0;
             atomicAdd(&D.counters[0], 1ull);   // CNT_FRAMES_DEMOD
@@ -623,6 +632,35 @@ __global__ void k_ofdm_gather_latest(const OfdmDev D, const int first_stream, in
     uint4* dst = reinterpret_cast<uint4*>(stage + size_t(blockIdx.y) * D.g.frame_bits);
     const int n16 = D.g.frame_bits / 16;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// OFDM_Demod::GetFrameFFT (ofdm_demodulator.h:135, filled by PipelineThread, ofdm_demodulator.cpp:673-700): the spectra of the
+// PRS and the data symbols of the last emitted frame, natural bin order, recomputed on demand from the IQ that is still in the
+// ring (the demodulation kernel keeps its spectra in registers).  One CTA per symbol; same PLL and FFT as the control kernel.
+template <int N>
+__global__ void __launch_bounds__(N / 8) k_ofdm_diag_fft(const OfdmDev D, const int s, float2* __restrict__ out) {
+    constexpr int NT = N / 8;
+    constexpr int NP = N + N / 8;
+    __shared__ float a_re[NP], a_im[NP];
+    const OfdmDiagMeta m = D.diag_meta[s];
+    if (!m.valid) return;
+    const OfdmGeom& g = D.g;
+    const int l = blockIdx.x, tid = threadIdx.x;
+    const float dt0 = __fmul_rn(float(l * g.Tsym), m.f);
+    float2 x[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int n = g.CP + tid + j * NT;
+        x[j] = pll_rotate(ofdm_ring_sample(D, s, m.abs0 + (unsigned long long)(l * g.Tsym + n)), n, m.f, dt0);
+    }
+    fft_cta<N, false>(x, a_re, a_im, D.tw, tid);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int i = tid + j * NT;
+        const int p = D.dpos[i];
+        out[size_t(l) * N + i] = make_float2(a_re[p], a_im[p]);
+    }
 }
 
 __global__ void k_ofdm_reset(const OfdmDev D, const int stream, const int n_streams, const int full) {

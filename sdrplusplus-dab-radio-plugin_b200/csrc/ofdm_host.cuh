@@ -16,7 +16,7 @@ struct OfdmState {
     size_t ring_cap = 0;          // internal ring capacity (samples)
     bool external_ring = false;
     int bps = 2;
-    DevBuf d_diag, d_ring, d_st, d_null_ring, d_corr, d_head, d_phase, d_tw, d_prs_conj, d_prs_time, d_dpos, d_outpos, d_obin, d_stage, d_produced;
+    DevBuf d_diag, d_diag_meta, d_diag_fft, d_ring, d_st, d_null_ring, d_corr, d_head, d_phase, d_tw, d_prs_conj, d_prs_time, d_dpos, d_outpos, d_obin, d_stage, d_produced;
     int num_sms = 148;
     // second stream: the streams of a launch are split in two groups so that the latency-bound control kernel of one
     // group overlaps the demodulation kernel of the other
@@ -102,6 +102,8 @@ static int ofdm_init(OfdmState& O, const dabgpu_config& cfg, const dabgpu_params
     if (cfg.flags & DABGPU_FLAG_DIAG_TAPS) {
         if ((rc = O.d_diag.alloc(size_t(S) * 2 * size_t(P.nb_fft) * sizeof(float)))) return rc;
         cudaMemset(O.d_diag.p, 0, O.d_diag.bytes);
+        if ((rc = O.d_diag_meta.alloc(size_t(S) * sizeof(OfdmDiagMeta)))) return rc;
+        cudaMemset(O.d_diag_meta.p, 0, O.d_diag_meta.bytes);
     }
     if ((rc = O.d_produced.alloc(size_t(S)))) return rc;
     if ((rc = O.h_produced.alloc(size_t(S)))) return rc;
@@ -218,6 +220,7 @@ static int ofdm_init(OfdmState& O, const dabgpu_config& cfg, const dabgpu_params
     D.head = O.d_head.as<float2>();
     D.phase_err = O.d_phase.as<float>();
     D.diag = O.d_diag.as<float>();   // null unless DABGPU_FLAG_DIAG_TAPS
+    D.diag_meta = O.d_diag_meta.as<OfdmDiagMeta>();
     D.tw = O.d_tw.as<float2>();
     D.prs_fft_conj = O.d_prs_conj.as<float2>();
     D.prs_time_ref = O.d_prs_time.as<float2>();
@@ -244,7 +247,7 @@ static int ofdm_init(OfdmState& O, const dabgpu_config& cfg, const dabgpu_params
 }
 
 static void ofdm_destroy(OfdmState& O) {
-    DevBuf* bufs[] = {&O.d_diag, &O.d_ring, &O.d_st, &O.d_null_ring, &O.d_corr, &O.d_head, &O.d_phase, &O.d_tw, &O.d_prs_conj, &O.d_prs_time,
+    DevBuf* bufs[] = {&O.d_diag, &O.d_diag_meta, &O.d_diag_fft, &O.d_ring, &O.d_st, &O.d_null_ring, &O.d_corr, &O.d_head, &O.d_phase, &O.d_tw, &O.d_prs_conj, &O.d_prs_time,
                       &O.d_dpos, &O.d_outpos, &O.d_obin, &O.d_stage, &O.d_produced};
     for (DevBuf* b : bufs) b->release();
     if (O.aux_stream) { cudaStreamSynchronize(O.aux_stream); cudaStreamDestroy(O.aux_stream); O.aux_stream = nullptr; }
@@ -450,6 +453,31 @@ static int ofdm_get_status(OfdmState& O, int stream, dabgpu_ofdm_status* out, cu
     out->freq_coarse_offset = st.coarse;
     out->freq_fine_offset = st.fine;
     out->frames_queued = 0;
+    return DABGPU_OK;
+}
+
+// GetFrameFFT tap: L x N complex spectra of the last emitted frame of one stream; DABGPU_ERR_STATE when no frame was emitted yet
+// or the frame was not contiguous in the ring (the first frame after an acquisition)
+static int ofdm_frame_fft(OfdmState& O, int stream, float* host_out, cudaStream_t cs) {
+    if (!O.d_diag_meta.p) return set_error(DABGPU_ERR_STATE, "context was created without DABGPU_FLAG_DIAG_TAPS");
+    const int L = O.P.nb_frame_symbols, N = O.P.nb_fft;
+    int rc;
+    if ((rc = O.d_diag_fft.alloc(size_t(L) * N * sizeof(float2)))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    OfdmDiagMeta m;
+    CUDA_TRY(cudaMemcpy(&m, O.d_diag_meta.as<OfdmDiagMeta>() + stream, sizeof(m), cudaMemcpyDeviceToHost));
+    if (!m.valid) return set_error(DABGPU_ERR_STATE, "no frame spectrum available for stream %d yet", stream);
+    float2* out = O.d_diag_fft.as<float2>();
+    switch (N) {
+    case 2048: k_ofdm_diag_fft<2048><<<L, 256, 0, cs>>>(O.dev, stream, out); break;
+    case 1024: k_ofdm_diag_fft<1024><<<L, 128, 0, cs>>>(O.dev, stream, out); break;
+    case 512: k_ofdm_diag_fft<512><<<L, 64, 0, cs>>>(O.dev, stream, out); break;
+    default: k_ofdm_diag_fft<256><<<L, 32, 0, cs>>>(O.dev, stream, out); break;
+    }
+    O.launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(host_out, out, size_t(L) * N * sizeof(float2), cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaStreamSynchronize(cs));
     return DABGPU_OK;
 }
 

@@ -214,7 +214,7 @@ def test_pipelined_submit_wait_equals_synchronous_process(gpu_ctx, tx, pyref):
 
 @pytest.mark.parametrize("mode", [1, 2])
 def test_gui_taps_match_reference(gpu_ctx, tx, pyref, ref_ok, mode):
-    """SURVEY section 8(f) rank 4 (partial): OFDM_Demod::GetImpulseResponse / GetCoarseFrequencyResponse served from device buffers.
+    """SURVEY section 8(f) rank 4: OFDM_Demod::GetImpulseResponse / GetCoarseFrequencyResponse / GetFrameFFT served from device buffers.
     The responses are float32 dB values behind different FFT implementations: the peak must sit at the same index and every bin
     within 40 dB of the peak must agree to 0.05 dB."""
     block = 65536
@@ -232,7 +232,15 @@ def test_gui_taps_match_reference(gpu_ctx, tx, pyref, ref_ok, mode):
         assert int(np.argmax(got)) == int(np.argmax(exp)), kind
         strong = exp > exp.max() - 40.0
         assert strong.sum() > 0 and np.abs(got[strong] - exp[strong]).max() < 0.05, (kind, np.abs(got[strong] - exp[strong]).max())
+    # OFDM_Demod::GetFrameFFT: PRS + data symbol spectra of the last emitted frame (the reference appends the NULL symbol row)
+    L = g.P.nb_frame_symbols
+    exp_fft = ref.frame_fft((L + 1) * n).reshape(L + 1, n)[:L]
+    got_fft = g.ofdm_frame_fft(0)
+    scale = np.abs(exp_fft).max()
+    assert scale > 0 and np.abs(got_fft - exp_fft).max() < 2e-3 * scale, np.abs(got_fft - exp_fft).max() / scale
     with pytest.raises(gpu_ctx.DabGpuError):
         plain.ofdm_response(0, 0)        # taps are opt-in: the context was created without the flag
+    with pytest.raises(gpu_ctx.DabGpuError):
+        plain.ofdm_frame_fft(0)
     g.close()
     plain.close()
