@@ -52,8 +52,12 @@ struct dabgpu_ctx {
     PinnedBuf h_status, h_stage;
     std::vector<uint32_t> h_frames_popped;   // per stream, host side cursor of dabgpu_ofdm_pop_frames
 
-    // DAB+ superframe stage
+    // DAB+ superframe stage.  It runs on its own stream so that it overlaps the OFDM stage of the next step (nothing on the
+    // main stream needs its results before the next channel decode or a getter): join_dabplus() makes the main stream wait.
     DabPlusState dabplus;
+    cudaStream_t s_dp = nullptr;
+    cudaEvent_t ev_dp = nullptr, ev_dp_fork = nullptr;
+    bool dp_pending = false;
 
     // OFDM
     OfdmState ofdm;
@@ -71,6 +75,18 @@ struct dabgpu_ctx {
 };
 
 static bool is_pow2(size_t v) { return v && !(v & (v - 1)); }
+
+// the main stream waits for the DAB+ kernel of the last channel decode (if it is still running on its own stream)
+static cudaError_t join_dabplus(dabgpu_ctx* ctx) {
+    if (!ctx->dp_pending) return cudaSuccess;
+    ctx->dp_pending = false;
+    return cudaStreamWaitEvent(ctx->stream, ctx->ev_dp, 0);
+}
+static cudaError_t sync_ctx(dabgpu_ctx* ctx) {
+    cudaError_t e = join_dabplus(ctx);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(ctx->stream);
+}
 
 extern "C" {
 
@@ -117,7 +133,7 @@ static int ensure_scratch(dabgpu_ctx* ctx, uint32_t steps) {
     if (steps <= ctx->scratch_steps) return DABGPU_OK;
     const uint32_t rounded = (steps + 63u) & ~63u;
     const size_t slots = size_t(ctx->vit_blocks) * VIT_WARPS_PER_BLOCK;
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     int rc = ctx->d_scratch.alloc(slots * rounded * sizeof(uint2));
     if (rc) return rc;
     ctx->scratch_steps = rounded;
@@ -249,6 +265,14 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
     C.counters = ctx->d_counters.as<unsigned long long>();
 
     TRY_OR_FREE(dabplus_init(ctx->dabplus, S, ctx->max_subs, P.nb_cifs));
+    if (getenv("DABGPU_DABPLUS_INLINE") == nullptr) {   // A/B switch: keep the DAB+ kernel on the main stream
+        if (cudaStreamCreateWithFlags(&ctx->s_dp, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_dp, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_dp_fork, cudaEventDisableTiming) != cudaSuccess) {
+            rc = set_error(DABGPU_ERR_CUDA, "DAB+ stream / event creation failed");
+            dabgpu_ctx_destroy(ctx);
+            return rc;
+        }
+    }
     ctx->ofdm.prof = &ctx->prof;
     TRY_OR_FREE(ofdm_init(ctx->ofdm, ctx->cfg, P, ctx->frame_slots, ctx->d_frames.as<int8_t>(), ctx->d_frames_written.as<uint32_t>(),
                           ctx->d_frame_info.as<dabgpu_frame_info>(), ctx->d_counters.as<unsigned long long>()));
@@ -261,7 +285,7 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
 void dabgpu_ctx_destroy(dabgpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) sync_ctx(ctx);
     ctx->prof.destroy();
     for (auto& sl : ctx->pipe) {
         if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
@@ -270,6 +294,9 @@ void dabgpu_ctx_destroy(dabgpu_ctx* ctx) {
         sl.d_stage.release();
         sl.d_produced.release();
     }
+    if (ctx->s_dp) { cudaStreamSynchronize(ctx->s_dp); cudaStreamDestroy(ctx->s_dp); }
+    if (ctx->ev_dp) cudaEventDestroy(ctx->ev_dp);
+    if (ctx->ev_dp_fork) cudaEventDestroy(ctx->ev_dp_fork);
     if (ctx->s_h2d) { cudaStreamSynchronize(ctx->s_h2d); cudaStreamDestroy(ctx->s_h2d); }
     if (ctx->s_d2h) { cudaStreamSynchronize(ctx->s_d2h); cudaStreamDestroy(ctx->s_d2h); }
     ofdm_destroy(ctx->ofdm);
@@ -287,7 +314,7 @@ void dabgpu_ctx_destroy(dabgpu_ctx* ctx) {
 
 int dabgpu_sync(dabgpu_ctx* ctx) {
     if (!ctx) return set_error(DABGPU_ERR_INVALID, "null context");
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     return DABGPU_OK;
 }
 
@@ -305,7 +332,7 @@ int dabgpu_profile_enable(dabgpu_ctx* ctx, int on) {
 int dabgpu_profile_read(dabgpu_ctx* ctx, dabgpu_profile* out) {
     if (!ctx || !out) return set_error(DABGPU_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     ctx->prof.collect();
     for (int i = 0; i < PROF_CLASSES; i++) { out->ms[i] = ctx->prof.ms[i]; out->launches[i] = ctx->prof.n[i]; }
     return DABGPU_OK;
@@ -350,14 +377,14 @@ static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, 
             lanes_wide = ctx->vl_ctas_forced == 4 || (ctx->vl_ctas_forced == 0 && groups > uint32_t(ctx->num_sms) * VL_WARPS_PER_BLOCK * 2u);
             const uint32_t need_slots = uint32_t(ctx->num_sms) * VL_WARPS_PER_BLOCK * (lanes_wide ? 4u : 1u);
             if (need_rows > ctx->vl_scratch_rows || need_slots > ctx->vl_scratch_slots || !ctx->d_vlscratch.p) {
-                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                CUDA_TRY(sync_ctx(ctx));
                 const uint32_t r = std::max((need_rows + 255u) & ~255u, ctx->vl_scratch_rows);
                 const uint32_t sl = std::max(need_slots, ctx->vl_scratch_slots);
                 if ((rc = ctx->d_vlscratch.alloc(size_t(sl) * r * 32u * sizeof(uint2)))) return rc;
                 ctx->vl_scratch_rows = r;
                 ctx->vl_scratch_slots = sl;
             }
-            if (ctx->d_vllist.bytes < size_t(n_jobs) * 4 || ctx->d_vlsym.bytes < size_t(rows) * 128u) CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (ctx->d_vllist.bytes < size_t(n_jobs) * 4 || ctx->d_vlsym.bytes < size_t(rows) * 128u) CUDA_TRY(sync_ctx(ctx));
             if ((rc = ctx->d_vllist.alloc(size_t(n_jobs) * 4))) return rc;
             if ((rc = ctx->d_vlsym.alloc(size_t(rows) * 128u))) return rc;
             plan = ctx->d_vlplan.as<VlPlan>();
@@ -457,7 +484,7 @@ int dabgpu_viterbi_decode(dabgpu_ctx* ctx, const dabgpu_viterbi_job* jobs, int n
     if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), n_jobs, &vb))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_vout.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (path_error_host) CUDA_TRY(cudaMemcpyAsync(path_error_host, ctx->d_verr.p, size_t(n_jobs) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     return DABGPU_OK;
 }
 
@@ -522,7 +549,7 @@ int dabgpu_msc_configure(dabgpu_ctx* ctx, int stream, const dabgpu_subchannel* s
         hs.push_back(h);
     }
     if ((rc = ensure_scratch(ctx, max_steps))) return rc;
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     CUDA_TRY(cudaMemcpy(ctx->d_subcfg.as<SubCfgDev>() + size_t(stream) * ctx->max_subs, dev.data(), dev.size() * sizeof(SubCfgDev), cudaMemcpyHostToDevice));
     const uint32_t ns = uint32_t(n_subs);
     CUDA_TRY(cudaMemcpy(ctx->d_nsubs.as<uint32_t>() + stream, &ns, 4, cudaMemcpyHostToDevice));
@@ -541,7 +568,7 @@ int dabgpu_softbits_push(dabgpu_ctx* ctx, const int8_t* frames_host, size_t stri
     // BasicRadio::Process requires exactly nb_frame_bits per call (basic_radio.cpp:41-46): the caller passes whole frames
     const size_t fb = size_t(ctx->P.nb_frame_bits);
     if ((rc = ctx->h_stage.alloc(size_t(n) * 4 + 64))) return rc;
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     uint32_t* written = ctx->h_stage.as<uint32_t>();
     CUDA_TRY(cudaMemcpy(written, ctx->d_frames_written.as<uint32_t>() + first, size_t(n) * 4, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; i++) {
@@ -551,7 +578,7 @@ int dabgpu_softbits_push(dabgpu_ctx* ctx, const int8_t* frames_host, size_t stri
         written[i] += 1;
     }
     CUDA_TRY(cudaMemcpyAsync(ctx->d_frames_written.as<uint32_t>() + first, written, size_t(n) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     return DABGPU_OK;
 }
 
@@ -659,6 +686,7 @@ int dabgpu_chan_decode(dabgpu_ctx* ctx, int first, int n) {
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     const uint32_t total = uint32_t(n) * ctx->chan.jobs_per_stream;
     if ((rc = ctx->d_jobs.alloc(size_t(total) * sizeof(VitJobDev)))) return rc;
+    CUDA_TRY(join_dabplus(ctx));   // the DAB+ kernel of the previous call reads the buffers this call rewrites
     VlPlan* count_plan = (ctx->vl_mode != 2) ? ctx->d_vlplan.as<VlPlan>() : nullptr;
     ctx->prof.begin(PROF_CHAN_MISC, ctx->stream);
     if (count_plan) CUDA_TRY(cudaMemsetAsync(count_plan, 0, sizeof(VlPlan), ctx->stream));
@@ -681,7 +709,16 @@ int dabgpu_chan_decode(dabgpu_ctx* ctx, int first, int n) {
         vb.max_steps = ctx->vl_cache.max_steps;
         if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), int(total), &vb, count_plan != nullptr))) return rc;
     }
-    if ((rc = dabplus_run(ctx->dabplus, ctx->chan, first, n, ctx->stream, &ctx->launches, ctx->prof))) return rc;
+    if (ctx->s_dp && !ctx->prof.on) {
+        // fork: the superframe stage only needs the decoded bytes; it overlaps k_chan_finish and whatever the caller queues next
+        CUDA_TRY(cudaEventRecord(ctx->ev_dp_fork, ctx->stream));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_dp, ctx->ev_dp_fork, 0));
+        if ((rc = dabplus_run(ctx->dabplus, ctx->chan, first, n, ctx->s_dp, &ctx->launches, ctx->prof))) return rc;
+        CUDA_TRY(cudaEventRecord(ctx->ev_dp, ctx->s_dp));
+        ctx->dp_pending = true;
+    } else {
+        if ((rc = dabplus_run(ctx->dabplus, ctx->chan, first, n, ctx->stream, &ctx->launches, ctx->prof))) return rc;
+    }
     ctx->prof.begin(PROF_CHAN_MISC, ctx->stream);
     k_chan_finish<<<n, 32, 0, ctx->stream>>>(ctx->chan, first, n);
     ctx->prof.end(ctx->stream);
@@ -694,7 +731,7 @@ int dabgpu_chan_get_status(dabgpu_ctx* ctx, int stream, dabgpu_chan_status* out)
     int rc = check_stream_range(ctx, stream, 1);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     int32_t st[2];
     CUDA_TRY(cudaMemcpy(st, ctx->d_status.as<int32_t>() + 2 * stream, 8, cudaMemcpyDeviceToHost));
     out->decoded = st[0];
@@ -706,7 +743,7 @@ int dabgpu_chan_get_fic(dabgpu_ctx* ctx, int stream, uint8_t* fibs_host, uint8_t
     int rc = check_stream_range(ctx, stream, 1);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     const int nb_cifs = ctx->P.nb_cifs, nf = ctx->P.nb_fibs_per_cif;
     std::vector<uint8_t> tmp(size_t(nb_cifs) * FIC_GROUP_BYTES), crc(size_t(nb_cifs) * 4);
     CUDA_TRY(cudaMemcpy(tmp.data(), ctx->d_fic_out.as<uint8_t>() + size_t(stream) * nb_cifs * FIC_GROUP_BYTES, tmp.size(), cudaMemcpyDeviceToHost));
@@ -728,7 +765,7 @@ int dabgpu_chan_get_msc(dabgpu_ctx* ctx, int stream, int sub_index, uint8_t* out
     if (bytes_per_cif) *bytes_per_cif = int(h.n_out_bytes);
     if (out_host && out_cap < size_t(nb_cifs) * h.n_out_bytes) return set_error(DABGPU_ERR_OVERFLOW, "output buffer too small");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     for (int c = 0; c < nb_cifs; c++) {
         if (out_host)
             CUDA_TRY(cudaMemcpy(out_host + size_t(c) * h.n_out_bytes,
@@ -746,7 +783,7 @@ int dabgpu_chan_get_dabplus_events(dabgpu_ctx* ctx, int stream, int sub_index, u
     if (rc) return rc;
     if (sub_index < 0 || size_t(sub_index) >= ctx->subs[size_t(stream)].size()) return set_error(DABGPU_ERR_INVALID, "sub-channel index %d not configured", sub_index);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     return dabplus_get_events(ctx->dabplus, stream, sub_index, log_host, log_cap, log_bytes);
 }
 
@@ -790,7 +827,7 @@ int dabgpu_fic_decode(dabgpu_ctx* ctx, const int8_t* soft_host, int n_groups, ui
     }
     std::vector<uint8_t> tmp(n * (FIC_GROUP_BYTES + 4));
     CUDA_TRY(cudaMemcpyAsync(tmp.data(), ctx->d_vout.p, tmp.size(), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     for (size_t i = 0; i < n; i++) {
         memcpy(fibs_host + i * 96, tmp.data() + i * FIC_GROUP_BYTES, 96);
         memcpy(crc_ok + i * 3, tmp.data() + n * FIC_GROUP_BYTES + i * 4, 3);
@@ -813,7 +850,7 @@ int dabgpu_dabplus_open(dabgpu_ctx* ctx, dabgpu_dabplus** out) {
 
 void dabgpu_dabplus_close(dabgpu_ctx* ctx, dabgpu_dabplus* p) {
     if (!p) return;
-    if (ctx) { cudaSetDevice(ctx->cfg.device); cudaStreamSynchronize(ctx->stream); }
+    if (ctx) { cudaSetDevice(ctx->cfg.device); sync_ctx(ctx); }
     if (p->d) cudaFree(p->d);
     delete p;
 }
@@ -828,7 +865,7 @@ int dabgpu_dabplus_process(dabgpu_ctx* ctx, dabgpu_dabplus* p, const uint8_t* fr
     CUDA_TRY(cudaGetLastError());
     int32_t n_ev = 0;
     CUDA_TRY(cudaMemcpyAsync(&n_ev, &p->d->n_events, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     if (n_ev > DP_MAX_EVENTS) return set_error(DABGPU_ERR_OVERFLOW, "event queue overflow (%d events)", n_ev);
     DabPlusEvent ev[DP_MAX_EVENTS];
     if (n_ev > 0) CUDA_TRY(cudaMemcpy(ev, p->d->events, size_t(n_ev) * sizeof(DabPlusEvent), cudaMemcpyDeviceToHost));
@@ -854,7 +891,7 @@ int dabgpu_dabplus_process(dabgpu_ctx* ctx, dabgpu_dabplus* p, const uint8_t* fr
 int dabgpu_get_counters(dabgpu_ctx* ctx, dabgpu_counters* out) {
     if (!ctx || !out) return set_error(DABGPU_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     unsigned long long c[CNT_COUNT];
     CUDA_TRY(cudaMemcpy(c, ctx->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
     out->frames_demodulated = c[CNT_FRAMES_DEMOD];
@@ -916,7 +953,7 @@ int dabgpu_ofdm_get_response(dabgpu_ctx* ctx, int stream, int kind, float* out, 
     if (!ctx->ofdm.d_diag.p) return set_error(DABGPU_ERR_STATE, "context was created without DABGPU_FLAG_DIAG_TAPS");
     if (n_floats < ctx->P.nb_fft) return set_error(DABGPU_ERR_OVERFLOW, "response needs %d floats", ctx->P.nb_fft);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     CUDA_TRY(cudaMemcpy(out, ctx->ofdm.d_diag.as<float>() + (size_t(stream) * 2 + size_t(kind)) * size_t(ctx->P.nb_fft), size_t(ctx->P.nb_fft) * sizeof(float),
                         cudaMemcpyDeviceToHost));
     return DABGPU_OK;
@@ -950,7 +987,7 @@ int dabgpu_ofdm_pop_frames(dabgpu_ctx* ctx, int stream, int8_t* frames_host, int
     if (rc) return rc;
     if (!n_out) return set_error(DABGPU_ERR_INVALID, "null output");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(sync_ctx(ctx));
     uint32_t written = 0;
     CUDA_TRY(cudaMemcpy(&written, ctx->d_frames_written.as<uint32_t>() + stream, 4, cudaMemcpyDeviceToHost));
     uint32_t& popped = ctx->h_frames_popped[size_t(stream)];
@@ -1031,6 +1068,7 @@ int dabgpu_submit(dabgpu_ctx* ctx, const dabgpu_step* st, uint64_t* ticket) {
         if ((rc = ofdm_gather_latest(O, first, n, sl.d_stage.as<int8_t>(), sl.d_produced.as<uint8_t>(), ctx->stream))) return rc;
     }
     if (st->run_chan_decode && (rc = dabgpu_chan_decode(ctx, first, n))) return rc;
+    CUDA_TRY(join_dabplus(ctx));
     CUDA_TRY(cudaEventRecord(sl.compute_done, ctx->stream));
     // (3) copy out.  The next compute may overwrite the channel-decode arenas: it is made to wait for this copy.
     CUDA_TRY(cudaStreamWaitEvent(ctx->s_d2h, sl.compute_done, 0));
