@@ -52,9 +52,9 @@ struct dabgpu_ctx {
     PinnedBuf h_status, h_stage;
     std::vector<uint32_t> h_frames_popped;   // per stream, host side cursor of dabgpu_ofdm_pop_frames
 
-    // DAB+ superframe stage.  It runs on its own stream so that it overlaps the OFDM stage of the next step (nothing on the
-    // main stream needs its results before the next channel decode or a getter): join_dabplus() makes the main stream wait.
+    // DAB+ superframe stage
     DabPlusState dabplus;
+    // channel stream: dabgpu_chan_decode runs on it (see there); join_dabplus() makes the main stream wait for it
     cudaStream_t s_dp = nullptr;
     cudaEvent_t ev_dp = nullptr, ev_dp_fork = nullptr;
     bool dp_pending = false;
@@ -76,7 +76,7 @@ struct dabgpu_ctx {
 
 static bool is_pow2(size_t v) { return v && !(v & (v - 1)); }
 
-// the main stream waits for the DAB+ kernel of the last channel decode (if it is still running on its own stream)
+// the main stream waits for the last channel decode (if it is still running on the channel stream)
 static cudaError_t join_dabplus(dabgpu_ctx* ctx) {
     if (!ctx->dp_pending) return cudaSuccess;
     ctx->dp_pending = false;
@@ -265,7 +265,7 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
     C.counters = ctx->d_counters.as<unsigned long long>();
 
     TRY_OR_FREE(dabplus_init(ctx->dabplus, S, ctx->max_subs, P.nb_cifs));
-    if (getenv("DABGPU_DABPLUS_INLINE") == nullptr) {   // A/B switch: keep the DAB+ kernel on the main stream
+    if (getenv("DABGPU_CHAN_INLINE") == nullptr) {   // A/B switch: keep the channel decode on the main stream
         if (cudaStreamCreateWithFlags(&ctx->s_dp, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_dp, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->ev_dp_fork, cudaEventDisableTiming) != cudaSuccess) {
             rc = set_error(DABGPU_ERR_CUDA, "DAB+ stream / event creation failed");
@@ -431,6 +431,7 @@ int dabgpu_viterbi_decode(dabgpu_ctx* ctx, const dabgpu_viterbi_job* jobs, int n
     if (!ctx || !jobs || !soft_host || !out_host) return set_error(DABGPU_ERR_INVALID, "null argument");
     if (n_jobs <= 0) return DABGPU_OK;
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(join_dabplus(ctx));   // shares the job, plan and scratch buffers with a channel decode that may still be running
     int rc;
     if ((rc = ctx->d_vsoft.alloc(soft_bytes + 16))) return rc;
     if ((rc = ctx->d_vout.alloc(out_bytes + 16))) return rc;
@@ -679,14 +680,11 @@ int dabgpu_autocfg_apply(dabgpu_autocfg* a, dabgpu_ctx* ctx, int stream) {
     return 1;
 }
 
-int dabgpu_chan_decode(dabgpu_ctx* ctx, int first, int n) {
-    int rc = check_stream_range(ctx, first, n);
-    if (rc) return rc;
-    if (n == 0) return DABGPU_OK;
-    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+// The kernels of one channel decode, all on ctx->stream (which dabgpu_chan_decode points at the channel stream meanwhile).
+static int chan_decode_body(dabgpu_ctx* ctx, int first, int n) {
+    int rc;
     const uint32_t total = uint32_t(n) * ctx->chan.jobs_per_stream;
     if ((rc = ctx->d_jobs.alloc(size_t(total) * sizeof(VitJobDev)))) return rc;
-    CUDA_TRY(join_dabplus(ctx));   // the DAB+ kernel of the previous call reads the buffers this call rewrites
     VlPlan* count_plan = (ctx->vl_mode != 2) ? ctx->d_vlplan.as<VlPlan>() : nullptr;
     ctx->prof.begin(PROF_CHAN_MISC, ctx->stream);
     if (count_plan) CUDA_TRY(cudaMemsetAsync(count_plan, 0, sizeof(VlPlan), ctx->stream));
@@ -709,22 +707,42 @@ int dabgpu_chan_decode(dabgpu_ctx* ctx, int first, int n) {
         vb.max_steps = ctx->vl_cache.max_steps;
         if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), int(total), &vb, count_plan != nullptr))) return rc;
     }
-    if (ctx->s_dp && !ctx->prof.on) {
-        // fork: the superframe stage only needs the decoded bytes; it overlaps k_chan_finish and whatever the caller queues next
-        CUDA_TRY(cudaEventRecord(ctx->ev_dp_fork, ctx->stream));
-        CUDA_TRY(cudaStreamWaitEvent(ctx->s_dp, ctx->ev_dp_fork, 0));
-        if ((rc = dabplus_run(ctx->dabplus, ctx->chan, first, n, ctx->s_dp, &ctx->launches, ctx->prof))) return rc;
-        CUDA_TRY(cudaEventRecord(ctx->ev_dp, ctx->s_dp));
-        ctx->dp_pending = true;
-    } else {
-        if ((rc = dabplus_run(ctx->dabplus, ctx->chan, first, n, ctx->stream, &ctx->launches, ctx->prof))) return rc;
-    }
+    if ((rc = dabplus_run(ctx->dabplus, ctx->chan, first, n, ctx->stream, &ctx->launches, ctx->prof))) return rc;
     ctx->prof.begin(PROF_CHAN_MISC, ctx->stream);
     k_chan_finish<<<n, 32, 0, ctx->stream>>>(ctx->chan, first, n);
     ctx->prof.end(ctx->stream);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return DABGPU_OK;
+}
+
+// The channel decode of a step runs on its own CUDA stream so that it overlaps whatever the caller queues next on the main
+// stream -- in a receiver loop the OFDM stage of the next step.  The lane Viterbi leaves half of every sub-partition's issue
+// slots empty at 256 streams and the OFDM kernels are latency bound, so the two fill each other's gaps.  Hazards: the OFDM
+// stage writes the frame-ring slot of frame n+1 while the decode of frame n reads the slots n-4..n (the ring keeps two frames
+// of margin, see frame_slots); every other buffer of the channel decode is only touched on the channel stream.  The main
+// stream joins (join_dabplus) before the next channel decode -- which bounds the lead to one step --, before every
+// synchronising getter, before dabgpu_viterbi_decode / dabgpu_fic_decode (shared job and scratch buffers) and before the
+// pipeline's compute-done event.  While profiling, everything stays on the main stream.
+int dabgpu_chan_decode(dabgpu_ctx* ctx, int first, int n) {
+    int rc = check_stream_range(ctx, first, n);
+    if (rc) return rc;
+    if (n == 0) return DABGPU_OK;
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(join_dabplus(ctx));
+    const bool fork = ctx->s_dp != nullptr && !ctx->prof.on;
+    cudaStream_t main_stream = ctx->stream;
+    if (fork) {
+        CUDA_TRY(cudaEventRecord(ctx->ev_dp_fork, main_stream));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_dp, ctx->ev_dp_fork, 0));
+        ctx->stream = ctx->s_dp;
+    }
+    rc = chan_decode_body(ctx, first, n);
+    if (fork) {
+        ctx->stream = main_stream;
+        if (cudaEventRecord(ctx->ev_dp, ctx->s_dp) == cudaSuccess) ctx->dp_pending = true;
+    }
+    return rc;
 }
 
 int dabgpu_chan_get_status(dabgpu_ctx* ctx, int stream, dabgpu_chan_status* out) {
@@ -790,6 +808,7 @@ int dabgpu_chan_get_dabplus_events(dabgpu_ctx* ctx, int stream, int sub_index, u
 int dabgpu_rs_decode(dabgpu_ctx* ctx, uint8_t* codewords_host, int n_codewords, int nroots, int pad, int* counts_host, int* positions_host) {
     if (!ctx || !codewords_host || !counts_host) return set_error(DABGPU_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(join_dabplus(ctx));
     return dabplus_rs_decode_batch(ctx->dabplus, codewords_host, n_codewords, nroots, pad, counts_host, positions_host, ctx->stream, &ctx->launches);
 }
 
@@ -797,6 +816,7 @@ int dabgpu_fic_decode(dabgpu_ctx* ctx, const int8_t* soft_host, int n_groups, ui
     if (!ctx || !soft_host || !fibs_host || !crc_ok) return set_error(DABGPU_ERR_INVALID, "null argument");
     if (n_groups <= 0) return DABGPU_OK;
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(join_dabplus(ctx));
     int rc;
     const size_t n = size_t(n_groups);
     if ((rc = ctx->d_vsoft.alloc(n * 2304 + 16))) return rc;
