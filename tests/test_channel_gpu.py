@@ -74,6 +74,29 @@ def test_viterbi_long_trellis_and_renormalisation(gpu_ctx, tx, pyref, vit_flags)
     g.close()
 
 
+def test_viterbi_lane_plan_edge_cases(gpu_ctx, tx, pyref):
+    """The device-side plan of the lane path: many length classes with partial groups in one call, and a trellis longer than
+    the classes cover (>= 73728 steps), which must send the whole call back to the warp-per-trellis kernel."""
+    rng = np.random.default_rng(13)
+    port = pyref.PortViterbi()
+    g = gpu_ctx.DabGpu(mode=1, max_streams=1, flags=2)   # DABGPU_FLAG_VIT_LANES_ALWAYS
+    # 75 trellises of 15 different lengths (6 .. 9222 steps): every class ends in a partial group
+    segs = [[(24, 4 * n)] for n in (6, 7, 38, 262, 270, 774, 1030, 1542, 1548, 2054, 3078, 4102, 6150, 8198, 9222) for _ in range(5)]
+    softs = [rng.integers(-127, 128, size=sg[0][1]).astype(np.int8) for sg in segs]
+    outs, perr = g.viterbi_decode(softs, segs)
+    for i, (soft, sg) in enumerate(zip(softs, segs)):
+        exp, _, exp_err = port.decode(soft, sg)
+        assert np.array_equal(outs[i], exp) and int(perr[i]) == exp_err, i
+    # one oversize trellis next to short ones
+    segs = [[(24, 4 * 80006)], [(24, 4 * 774)], [(24, 4 * 1542)]]
+    softs = [rng.integers(-127, 128, size=sg[0][1]).astype(np.int8) for sg in segs]
+    outs, perr = g.viterbi_decode(softs, segs)
+    for i, (soft, sg) in enumerate(zip(softs, segs)):
+        exp, _, exp_err = port.decode(soft, sg)
+        assert np.array_equal(outs[i], exp) and int(perr[i]) == exp_err, i
+    g.close()
+
+
 def test_viterbi_bad_arguments(gpu_ctx, tx):
     g = gpu_ctx.DabGpu(mode=1, max_streams=1)
     soft = np.zeros(100, dtype=np.int8)
