@@ -6,11 +6,11 @@
 // dab/algorithms/dab_viterbi_decoder.cpp:109-181); the arithmetic is in viterbi_lane_core.h.
 //
 // Pipeline of one call (all on the context's stream, no host round trip):
-//   k_vit_count    histogram of the active trellises by length class
+//   k_vit_count    histogram of the active trellises by length class (dabgpu_chan_decode takes it in k_chan_build_jobs instead)
 //   k_vit_plan     one thread: decides lanes vs warps, orders the classes longest first, assigns symbol rows
 //   k_vit_scatter  job indices grouped by class (32 consecutive entries = one warp's trellises)
-//   k_vit_prep     time de-interleave + de-puncture (the loader of viterbi.cuh, unchanged) into a [step][lane] word matrix
-//                  per group, so that the decoder reads one coalesced 128-byte row per trellis step
+//   k_vit_prep     time de-interleave + de-puncture (the loader of viterbi.cuh with the puncturing segment cached per trellis)
+//                  into a [step][lane] word matrix per group, so that the decoder reads one coalesced 128-byte row per step
 //   k_viterbi_lanes  persistent warps: forward pass (decisions to a per-warp scratch, 256 B coalesced per step), traceback,
 //                  energy dispersal, FIB CRC
 #pragma once
