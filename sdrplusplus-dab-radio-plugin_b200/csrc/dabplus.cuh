@@ -119,6 +119,9 @@ struct DpShared {
     uint8_t gf_lg[256];
     uint16_t crc_ccitt[256];
     uint16_t crc_fire[256];
+    // branch-free x * alpha^r for the syndrome loop: gf_exz[gf_lgx[x] + r] with log(0) mapped past the end of the exp table
+    uint16_t gf_lgx[256];
+    uint8_t gf_exz[528];
     __align__(16) uint8_t sfbuf[DP_WARPS][DP_SF_SMEM];
 };
 
@@ -128,7 +131,9 @@ __device__ __forceinline__ void dp_load_shared(DpShared& sh) {
         sh.gf_lg[i] = c_gf_log[i];
         sh.crc_ccitt[i] = c_crc_ccitt[i];
         sh.crc_fire[i] = c_crc_fire[i];
+        sh.gf_lgx[i] = i ? uint16_t(c_gf_log[i]) : uint16_t(512);
     }
+    for (int i = threadIdx.x; i < 528; i += blockDim.x) sh.gf_exz[i] = (i < 510) ? c_gf_exp[i] : uint8_t(0);
     __syncthreads();
 }
 
@@ -186,7 +191,7 @@ __device__ void dp_superframe(DpShared& sh, uint8_t* sf_global, uint8_t* sf_out,
 #pragma unroll
                 for (int q = 0; q < 3; q++) {
                     const int r = part + 4 * q;   // root index; r >= 10 is computed but ignored
-                    Sp[q] = uint8_t(d ^ (Sp[q] ? T.ex[gf_mod255(T.lg[Sp[q]] + r)] : 0));
+                    Sp[q] = uint8_t(d ^ sh.gf_exz[sh.gf_lgx[Sp[q]] + r]);   // Horner step s = s * alpha^r + d (reed_solomon_decoder.cpp:223-240)
                 }
             }
         }
