@@ -256,3 +256,50 @@ def test_rs_batch_matches_oracle(gpu_ctx, tx, pyref):
         c, d, _ = o2.decode(cws2[t])
         assert counts2[t] == c and np.array_equal(fixed2[t], d), t
     g.close()
+
+
+def test_channel_stream_overlap_is_invisible(gpu_ctx, tx, pyref, monkeypatch):
+    """dabgpu_chan_decode runs on its own CUDA stream.  Every API that touches its buffers or results joins that stream first:
+    a context that keeps the channel decode on the main stream (DABGPU_CHAN_INLINE=1) and an overlapping one must return the
+    same bytes when other calls are squeezed between the decode and the getters."""
+    rng = np.random.default_rng(41)
+    subs = _subs(tx)
+    ens = tx.EnsembleTx(1, subs, seed=17)
+    frames = [tx.hard_to_soft(ens.next_frame_bits(), rng, snr_db=6.0)[None, :] for _ in range(8)]
+    monkeypatch.setenv("DABGPU_CHAN_INLINE", "1")
+    inline = gpu_ctx.DabGpu(mode=1, max_streams=1, flags=2)
+    monkeypatch.delenv("DABGPU_CHAN_INLINE")
+    overl = gpu_ctx.DabGpu(mode=1, max_streams=1, flags=2)
+    sg = tx.eep_segments(48, 2, False)
+    n_in = int(tx.puncture_mask(sg).sum())
+    port = pyref.PortViterbi()
+    for g in (inline, overl):
+        g.msc_configure(0, subs)
+    for f, frame in enumerate(frames):
+        res = []
+        for g in (inline, overl):
+            g.softbits_push(frame)
+            g.chan_decode()
+            extra = None
+            if f % 2 == 0:      # shares the job / plan / scratch buffers with the decode that may still be running
+                soft = np.random.default_rng(100 + f).integers(-127, 128, size=n_in).astype(np.int8)
+                outs, perr = g.viterbi_decode([soft] * 3, [sg] * 3)
+                exp, _, exp_err = port.decode(soft, sg)
+                assert all(np.array_equal(o, exp) for o in outs) and all(int(e) == exp_err for e in perr)
+                extra = outs[0]
+            if f == 5:
+                g.msc_configure(0, subs)   # reconfiguration while a decode may be in flight: de-interleavers restart
+            fibs, ok = g.get_fic(0)
+            item = [fibs.copy(), ok.copy()]
+            for k, sc in enumerate(subs):
+                out, valid = g.get_msc(0, k)
+                item += [valid.copy()] + [out[c].copy() for c in range(4) if valid[c]]
+                if sc.dabplus:
+                    item.append(np.frombuffer(g.get_dabplus_events(0, k), dtype=np.uint8).copy())
+            res.append(item)
+        assert len(res[0]) == len(res[1])
+        for a, b in zip(res[0], res[1]):
+            assert np.array_equal(a, b), f
+    assert inline.counters() == overl.counters()
+    inline.close()
+    overl.close()
