@@ -115,9 +115,10 @@ __device__ __forceinline__ void prep_seg_load(PrepSeg& S, const VitJobDev& J, co
 
 // One CTA per group; warp w fills the columns VP_JPW*w .. VP_JPW*w + VP_JPW-1 of the group's symbol matrix, lane = trellis
 // step within a chunk of 32.  The pass is a chain of dependent L2 round trips per warp (one per trellis and chunk: the byte
-// loads of a step are predicated on the puncturing count), so its time is (trellises per warp) x (chunks) x latency: two
-// trellises per warp and 16 warps per CTA instead of eight and four cut that chain by four.
-#define VP_JPW 2u
+// loads of a step are predicated on its puncturing count), so fewer trellises per warp shorten it, while more trellises
+// per warp give full-sector stores.  Measured per 256-stream step (planning kernels included): 8 per warp 0.294 ms,
+// 4 per warp 0.218 ms, 2 per warp 0.252 ms, 1 per warp 0.303 ms.
+#define VP_JPW 4u
 #define VP_WARPS (32u / VP_JPW)
 __global__ void __launch_bounds__(VP_WARPS * 32)
 k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, const uint32_t* __restrict__ list, uint32_t* __restrict__ sym, const GatherGeom G) {
@@ -184,7 +185,7 @@ k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, 
                 v[jj] = (t < sJ[q].total_steps) ? vit_load_step(sJ[q], s_rowoff[q], t) : 0u;
             }
         }
-        if (t < padded) *reinterpret_cast<uint2*>(dst + size_t(t) * 32u) = make_uint2(v[0], v[1]);
+        if (t < padded) *reinterpret_cast<uint4*>(dst + size_t(t) * 32u) = make_uint4(v[0], v[1], v[2], v[3]);
         // move the cached segments to the one that contains the first step of the next chunk
         __syncwarp();
         if (lane < VP_JPW) {
