@@ -62,7 +62,8 @@ typedef struct {
     int max_streams;       /* independent IQ streams held by this context */
     int iq_format;         /* DABGPU_IQ_U8 (2 B/sample, converted on device like app_iq_readers.h:23-43,72-87) or DABGPU_IQ_C32 */
     size_t ring_samples;   /* per-stream IQ ring capacity in samples, power of two; 0 = 4 frames rounded up */
-    int frame_slots;       /* soft-bit frame ring depth per stream (>= 8, power of two); 0 = 8 */
+    int frame_slots;       /* soft-bit frame ring depth per stream, power of two >= the 16-CIF de-interleaver history + 2 frames
+                              (8 in mode I, 16 in mode IV, 32 in modes II/III); 0 = twice that minimum */
     int max_subchannels;   /* sub-channel table size per stream; 0 = 64 */
     void* cuda_stream;     /* optional cudaStream_t owned by the caller; NULL = library creates one */
     dabgpu_ofdm_config ofdm;
@@ -118,6 +119,8 @@ typedef struct {
     float freq_coarse_offset;
     float freq_fine_offset;
     int frames_queued;         /* soft-bit frames produced and not yet popped */
+    int frames_dropped;        /* frames dabgpu_ofdm_pop_frames could not deliver because the caller fell more than frame_slots-1
+                                  frames behind and the ring slots were reused (the reference's observers never lose a frame) */
 } dabgpu_ofdm_status;
 
 /* OFDM_Demod::GetConfig() is mutable in the reference (the GUI edits it while running, ofdm_demodulator.h:122):
@@ -153,10 +156,19 @@ DABGPU_API int dabgpu_ofdm_get_status(dabgpu_ctx* ctx, int stream, dabgpu_ofdm_s
  * kind 1 = OFDM_Demod::GetCoarseFrequencyResponse (ofdm_demodulator.cpp:360-471), both read by the plugin's render code
  * (src/render_radio_block.cpp:192-214). */
 DABGPU_API int dabgpu_ofdm_get_response(dabgpu_ctx* ctx, int stream, int kind, float* out, int n_floats);
+/* OFDM_Demod::GetCorrelationTimeBuffer (ofdm_demodulator.h:139): the (nb_null_period + nb_symbol_period) complex<float> samples
+ * of the NULL symbol + PRS window the synchronisation works on (no flag needed: the control kernel keeps it anyway). */
+DABGPU_API int dabgpu_ofdm_get_correlation_buffer(dabgpu_ctx* ctx, int stream, float* out, size_t n_floats);
 /* OFDM_Demod::GetFrameFFT (ofdm_demodulator.h:135): nb_frame_symbols x nb_fft complex<float> spectra (PRS first, natural bin
- * order) of the last frame the stream emitted, recomputed on demand from the IQ still in the device ring.  The NULL-symbol row
- * the reference appends is not served.  DABGPU_ERR_STATE until a frame that lies contiguously in the ring has been emitted. */
+ * order) of the last frame the stream emitted, recomputed on demand from the IQ still in the device ring.  When n_floats has
+ * room for (nb_frame_symbols + 1) rows, the last row is the spectrum of the NULL symbol that follows the frame, as in the
+ * reference's buffer (ofdm_demodulator.cpp:108, 703-709).  DABGPU_ERR_STATE until a frame that lies contiguously in the ring has
+ * been emitted. */
 DABGPU_API int dabgpu_ofdm_get_frame_fft(dabgpu_ctx* ctx, int stream, float* out, size_t n_floats);
+/* OFDM_Demod::GetFrameDataVec (ofdm_demodulator.h:136, CalculateDQPSK ofdm_demodulator.cpp:842-865): (nb_frame_symbols - 1) x
+ * nb_data_carriers complex<float> differential vectors X_i * conj(X_{i+1}) of the same frame, carriers -K/2..K/2 without DC,
+ * before the frequency de-interleaver (the constellation the GUI plots). */
+DABGPU_API int dabgpu_ofdm_get_frame_data_vec(dabgpu_ctx* ctx, int stream, float* out, size_t n_floats);
 DABGPU_API int dabgpu_ofdm_pop_frames(dabgpu_ctx* ctx, int stream, int8_t* frames_host, int max_frames,
                                       dabgpu_frame_info* infos, int* n_frames_out);
 /* Bulk variant used by throughput harnesses: newest frame of every stream in [first, first+n) that
@@ -246,10 +258,19 @@ typedef struct {
     int is_dabplus;      /* run the DAB+ superframe stage on this sub-channel */
 } dabgpu_subchannel;
 
-/* (Re)creates the MSC_Decoder set of one stream; deinterleaver / superframe state starts empty. */
+/* Declares the MSC_Decoder set of one stream.  Entries that are identical to the entry with the same index of the previous
+ * table keep their time de-interleaver and superframe state (BasicRadio never disturbs a running decoder, basic_radio.cpp:98-131);
+ * every other entry starts empty like a new MSC_Decoder / AAC_Frame_Processor. */
 DABGPU_API int dabgpu_msc_configure(dabgpu_ctx* ctx, int stream, const dabgpu_subchannel* subs, int n_subs);
+/* BasicRadio::UpdateAfterProcessing (basic_radio/basic_radio.cpp:83-154): attach a decoder to one newly complete sub-channel;
+ * the decoders already running are not touched.  *sub_index_out = index of the new entry. */
+DABGPU_API int dabgpu_msc_add_subchannel(dabgpu_ctx* ctx, int stream, const dabgpu_subchannel* sub, int* sub_index_out);
+/* Detach one decoder; the other entries keep their indices and state (no reference analogue: BasicRadio only ever adds). */
+DABGPU_API int dabgpu_msc_remove_subchannel(dabgpu_ctx* ctx, int stream, int sub_index);
 
-/* BasicRadio::Process: one frame of nb_frame_bits int8 per stream, stream i at frames_host + i*stride */
+/* BasicRadio::Process: one frame of nb_frame_bits int8 per stream, stream i at frames_host + i*stride.  DABGPU_ERR_OVERFLOW when
+ * the frame ring of a stream is full of frames that were not channel-decoded yet (the reference's ThreadedRingBuffer blocks its
+ * producer in that case, src/radio_block.cpp:20-44). */
 DABGPU_API int dabgpu_softbits_push(dabgpu_ctx* ctx, const int8_t* frames_host, size_t stream_stride_bytes,
                                     int first_stream, int n_streams);
 
@@ -275,9 +296,12 @@ DABGPU_API int dabgpu_autocfg_push_fibs(dabgpu_autocfg* a, const uint8_t* fibs, 
 DABGPU_API int dabgpu_autocfg_dump(dabgpu_autocfg* a, int32_t* subs, int subs_cap_rows, int* n_subs, int32_t* comps, int comps_cap_rows, int* n_comps);
 /* The sub-channels BasicRadio would attach an audio decoder to, in database order; ids[i] = SubChId of out[i]. */
 DABGPU_API int dabgpu_autocfg_runnable(dabgpu_autocfg* a, dabgpu_subchannel* out, uint8_t* ids, int cap, int* n_out);
-/* dabgpu_msc_configure(ctx, stream, runnable set) when the set differs from the one applied last; returns 1 if it
- * reconfigured, 0 if nothing changed, negative on error. */
+/* BasicRadio::UpdateAfterProcessing: dabgpu_msc_add_subchannel(ctx, stream, ...) for every sub-channel that became runnable since
+ * the last call; running decoders are not touched.  Sub-channels the context rejects (invalid range / profile) are skipped for
+ * good and do not block the others.  Returns 1 if a decoder was added, 0 if nothing changed, negative on error.  One autocfg
+ * object serves one (ctx, stream) pair.  dabgpu_autocfg_applied: SubChId of every sub_index it created, in order. */
 DABGPU_API int dabgpu_autocfg_apply(dabgpu_autocfg* a, dabgpu_ctx* ctx, int stream);
+DABGPU_API int dabgpu_autocfg_applied(dabgpu_autocfg* a, uint8_t* ids, int cap, int* n_out);
 
 /* ---------------------------------------------------------------------------------------------
  * Capture file formats of the reference's tools (host only): raw IQ in the reader modes of
@@ -295,8 +319,14 @@ DABGPU_API int dabgpu_softbits_to_bytes(const int8_t* bits, size_t n_bits, uint8
 DABGPU_API int dabgpu_bytes_to_softbits(const uint8_t* bytes, size_t n_bytes, int8_t* bits);
 
 /* Decodes, for every stream in [first, first+n), the oldest frame in its ring that has not been
- * channel-decoded yet (streams without one are skipped).  Results stay on the device until fetched. */
+ * channel-decoded yet (streams without one are skipped).  Results stay on the device until fetched.
+ * A stream whose decoder fell further behind than the ring keeps history for (frame_slots minus the 16-CIF history minus two
+ * frames of margin) skips to its newest frame and restarts its time de-interleavers empty; the skipped frames are counted in
+ * dabgpu_counters.frames_dropped.  Stale ring slots are never decoded. */
 DABGPU_API int dabgpu_chan_decode(dabgpu_ctx* ctx, int first_stream, int n_streams);
+/* dabgpu_chan_decode runs on a CUDA stream of its own so that it overlaps the next OFDM stage.  Every getter of this library
+ * joins it implicitly; callers that queue their own work or events on dabgpu_cuda_stream() call this (non-blocking) first. */
+DABGPU_API int dabgpu_chan_join(dabgpu_ctx* ctx);
 
 /* Result of the last dabgpu_chan_decode for one stream. */
 typedef struct {
@@ -342,6 +372,7 @@ typedef struct {
     uint64_t msc_bytes_decoded;
     uint64_t superframes_ok, superframes_rs_fail, superframes_firecode_fail;
     uint64_t au_ok, au_crc_fail;
+    uint64_t frames_dropped;       /* frames the channel decoder skipped because it fell behind the frame ring (see dabgpu_chan_decode) */
 } dabgpu_counters;
 DABGPU_API int dabgpu_get_counters(dabgpu_ctx* ctx, dabgpu_counters* out);
 

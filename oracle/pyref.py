@@ -95,6 +95,10 @@ class RefLib:
         L.ref_ofdm_set_coarse_enabled.argtypes = [C.c_void_p, C.c_int]
         L.ref_ofdm_get_frame_fft.argtypes = [C.c_void_p, _f32p, C.c_int]
         L.ref_ofdm_get_impulse_response.argtypes = [C.c_void_p, _f32p, C.c_int]
+        if hasattr(L, "ref_ofdm_get_correlation_buffer"):
+            L.ref_ofdm_get_correlation_buffer.argtypes = [C.c_void_p, _f32p, C.c_int]
+        if hasattr(L, "ref_ofdm_get_frame_data_vec"):
+            L.ref_ofdm_get_frame_data_vec.argtypes = [C.c_void_p, _f32p, C.c_int]
         L.ref_ofdm_get_coarse_response.argtypes = [C.c_void_p, _f32p, C.c_int]
         L.ref_time_ofdm_u8.argtypes = [C.c_int, _u8p, C.c_long, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.ref_time_ofdm_u8.restype = C.c_double
@@ -362,6 +366,16 @@ class RefOfdm:
         out = np.zeros(2 * n_complex, dtype=np.float32)
         self.lib.ref_ofdm_get_frame_fft(self.h, out, n_complex)
         return out.view(np.complex64)
+
+    def frame_data_vec(self, n_complex: int) -> np.ndarray:
+        out = np.zeros(2 * n_complex, dtype=np.float32)
+        self.lib.ref_ofdm_get_frame_data_vec(self.h, out, n_complex)
+        return out.view(np.complex64)
+
+    def correlation_buffer(self, n_complex: int) -> np.ndarray:
+        out = np.zeros(2 * n_complex, dtype=np.float32)
+        n = self.lib.ref_ofdm_get_correlation_buffer(self.h, out, n_complex)
+        return out.view(np.complex64)[:n]
 
     def impulse_response(self, n: int) -> np.ndarray:
         out = np.zeros(n, dtype=np.float32)

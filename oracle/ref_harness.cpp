@@ -449,6 +449,17 @@ API void ref_ofdm_get_frame_fft(void* h, float* out, int n_complex) {
     const size_t n = (size_t(n_complex) < s.size()) ? size_t(n_complex) : s.size();
     memcpy(out, s.data(), n*sizeof(std::complex<float>));
 }
+API void ref_ofdm_get_frame_data_vec(void* h, float* out, int n_complex) {
+    auto s = ((RefOfdm*)h)->demod->GetFrameDataVec();
+    const size_t n = (size_t(n_complex) < s.size()) ? size_t(n_complex) : s.size();
+    memcpy(out, s.data(), n*sizeof(std::complex<float>));
+}
+API int ref_ofdm_get_correlation_buffer(void* h, float* out, int n_complex) {
+    auto s = ((RefOfdm*)h)->demod->GetCorrelationTimeBuffer();
+    const size_t n = (size_t(n_complex) < s.size()) ? size_t(n_complex) : s.size();
+    memcpy(out, s.data(), n*sizeof(std::complex<float>));
+    return int(n);
+}
 API void ref_ofdm_get_impulse_response(void* h, float* out, int n) {
     auto s = ((RefOfdm*)h)->demod->GetImpulseResponse();
     const size_t m = (size_t(n) < s.size()) ? size_t(n) : s.size();

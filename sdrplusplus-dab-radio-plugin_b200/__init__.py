@@ -50,7 +50,7 @@ class Params(C.Structure):
 class OfdmStatus(C.Structure):
     _fields_ = [("state", C.c_int), ("total_frames_read", C.c_int), ("total_frames_desync", C.c_int), ("fine_time_offset", C.c_int),
                 ("signal_l1_average", C.c_float), ("freq_coarse_offset", C.c_float), ("freq_fine_offset", C.c_float),
-                ("frames_queued", C.c_int)]
+                ("frames_queued", C.c_int), ("frames_dropped", C.c_int)]
 
 
 class FrameInfo(C.Structure):
@@ -72,7 +72,8 @@ class ChanStatus(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("frames_demodulated", "frames_channel_decoded", "fibs_crc_ok", "fibs_total", "msc_bytes_decoded",
-                                          "superframes_ok", "superframes_rs_fail", "superframes_firecode_fail", "au_ok", "au_crc_fail")]
+                                          "superframes_ok", "superframes_rs_fail", "superframes_firecode_fail", "au_ok", "au_crc_fail",
+                                          "frames_dropped")]
 
 
 class Profile(C.Structure):
@@ -101,6 +102,7 @@ EXPORTS = [
     "dabgpu_get_counters", "dabgpu_submit", "dabgpu_wait", "dabgpu_msc_get_layout",
     "dabgpu_ofdm_set_config", "dabgpu_fic_decode", "dabgpu_dabplus_open", "dabgpu_dabplus_close", "dabgpu_dabplus_process",
     "dabgpu_autocfg_create", "dabgpu_autocfg_destroy", "dabgpu_autocfg_push_fibs", "dabgpu_autocfg_dump", "dabgpu_autocfg_runnable",
+    "dabgpu_ofdm_get_frame_data_vec", "dabgpu_ofdm_get_correlation_buffer", "dabgpu_autocfg_applied", "dabgpu_msc_add_subchannel", "dabgpu_msc_remove_subchannel", "dabgpu_chan_join",
     "dabgpu_autocfg_apply", "dabgpu_ofdm_get_response", "dabgpu_ofdm_get_frame_fft", "dabgpu_iq_convert", "dabgpu_softbits_to_bytes", "dabgpu_bytes_to_softbits",
 ]
 
@@ -139,6 +141,9 @@ def load_library() -> C.CDLL:
     L.dabgpu_ofdm_fetch_latest.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.dabgpu_viterbi_decode.argtypes = [C.c_void_p, C.POINTER(ViterbiJob), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
     L.dabgpu_msc_configure.argtypes = [C.c_void_p, C.c_int, C.POINTER(SubchannelC), C.c_int]
+    L.dabgpu_msc_add_subchannel.argtypes = [C.c_void_p, C.c_int, C.POINTER(SubchannelC), C.POINTER(C.c_int)]
+    L.dabgpu_msc_remove_subchannel.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.dabgpu_chan_join.argtypes = [C.c_void_p]
     L.dabgpu_softbits_push.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
     L.dabgpu_chan_decode.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.dabgpu_chan_get_status.argtypes = [C.c_void_p, C.c_int, C.POINTER(ChanStatus)]
@@ -163,8 +168,11 @@ def load_library() -> C.CDLL:
     L.dabgpu_autocfg_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.dabgpu_autocfg_runnable.argtypes = [C.c_void_p, C.POINTER(SubchannelC), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.dabgpu_autocfg_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.dabgpu_autocfg_applied.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.dabgpu_ofdm_get_response.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
     L.dabgpu_ofdm_get_frame_fft.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    L.dabgpu_ofdm_get_frame_data_vec.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    L.dabgpu_ofdm_get_correlation_buffer.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.dabgpu_iq_convert.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.dabgpu_softbits_to_bytes.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     L.dabgpu_bytes_to_softbits.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
@@ -272,15 +280,35 @@ class DabGpu:
         return [out[o:o + m].copy() for o, m in outs], perr
 
     # ---- channel decode ------------------------------------------------------------------
+    @staticmethod
+    def _fill_sub(dst: SubchannelC, s) -> None:
+        dst.start_address, dst.length = s.start_address, s.length
+        dst.is_uep, dst.uep_prot_index = int(s.is_uep), s.uep_index
+        dst.eep_prot_level, dst.eep_type_b = s.eep_level, int(s.eep_type_b)
+        dst.is_dabplus = int(getattr(s, "dabplus", False))
+
     def msc_configure(self, stream: int, subs: Sequence) -> None:
         arr = (SubchannelC * max(len(subs), 1))()
         for i, s in enumerate(subs):
-            arr[i].start_address, arr[i].length = s.start_address, s.length
-            arr[i].is_uep, arr[i].uep_prot_index = int(s.is_uep), s.uep_index
-            arr[i].eep_prot_level, arr[i].eep_type_b = s.eep_level, int(s.eep_type_b)
-            arr[i].is_dabplus = int(getattr(s, "dabplus", False))
+            self._fill_sub(arr[i], s)
         _check(self.L.dabgpu_msc_configure(self.h, stream, arr, len(subs)))
         self._subs[stream] = list(subs)
+
+    def msc_add_subchannel(self, stream: int, sub) -> int:
+        """Attach one more decoder without touching the running ones; returns its sub_index."""
+        d = SubchannelC()
+        self._fill_sub(d, sub)
+        idx = C.c_int(-1)
+        _check(self.L.dabgpu_msc_add_subchannel(self.h, stream, C.byref(d), C.byref(idx)))
+        self._subs.setdefault(stream, []).append(sub)
+        return idx.value
+
+    def msc_remove_subchannel(self, stream: int, sub_index: int) -> None:
+        _check(self.L.dabgpu_msc_remove_subchannel(self.h, stream, sub_index))
+
+    def chan_join(self) -> None:
+        """Non-blocking: work queued on the context's stream from now on waits for the last chan_decode."""
+        _check(self.L.dabgpu_chan_join(self.h))
 
     def softbits_push(self, frames: np.ndarray, first_stream: int = 0) -> None:
         """frames: [n_streams, nb_frame_bits] int8"""
@@ -416,10 +444,22 @@ class DabGpu:
         _check(self.L.dabgpu_ofdm_get_response(self.h, stream, kind, out.ctypes.data, out.size))
         return out
 
-    def ofdm_frame_fft(self, stream: int) -> np.ndarray:
-        """GUI tap: (nb_frame_symbols, nb_fft) complex64 spectra of the last emitted frame; needs FLAG_DIAG_TAPS."""
-        out = np.empty((self.P.nb_frame_symbols, self.P.nb_fft), dtype=np.complex64)
+    def ofdm_frame_fft(self, stream: int, with_null: bool = False) -> np.ndarray:
+        """GUI tap: (nb_frame_symbols [+ 1 NULL row], nb_fft) complex64 spectra of the last emitted frame; needs FLAG_DIAG_TAPS."""
+        out = np.empty((self.P.nb_frame_symbols + int(with_null), self.P.nb_fft), dtype=np.complex64)
         _check(self.L.dabgpu_ofdm_get_frame_fft(self.h, stream, out.ctypes.data, out.size * 2))
+        return out
+
+    def ofdm_correlation_buffer(self, stream: int) -> np.ndarray:
+        """GUI tap: the NULL + PRS correlation window, nb_null_period + nb_symbol_period complex64."""
+        out = np.empty(self.P.nb_null_period + self.P.nb_symbol_period, dtype=np.complex64)
+        _check(self.L.dabgpu_ofdm_get_correlation_buffer(self.h, stream, out.ctypes.data, out.size * 2))
+        return out
+
+    def ofdm_frame_data_vec(self, stream: int) -> np.ndarray:
+        """GUI tap: (nb_frame_symbols - 1, nb_data_carriers) complex64 DQPSK vectors of the last emitted frame."""
+        out = np.empty((self.P.nb_frame_symbols - 1, self.P.nb_data_carriers), dtype=np.complex64)
+        _check(self.L.dabgpu_ofdm_get_frame_data_vec(self.h, stream, out.ctypes.data, out.size * 2))
         return out
 
     def ofdm_pop_frames(self, stream: int, max_frames: int = 64):
@@ -482,6 +522,13 @@ class FicAutoConfig:
         _check(self.L.dabgpu_autocfg_runnable(self.h, arr, ids.ctypes.data, 64, C.byref(n)))
         out = [{f: getattr(arr[i], f) for f, _ in SubchannelC._fields_} for i in range(n.value)]
         return out, [int(x) for x in ids[:n.value]]
+
+    def applied(self) -> list:
+        """SubChIds that got a decoder through apply(), in sub_index order."""
+        ids = np.zeros(64, dtype=np.uint8)
+        n = C.c_int(0)
+        _check(self.L.dabgpu_autocfg_applied(self.h, ids.ctypes.data, 64, C.byref(n)))
+        return [int(x) for x in ids[:n.value]]
 
     def apply(self, ctx: "DabGpu", stream: int = 0) -> bool:
         rc = self.L.dabgpu_autocfg_apply(self.h, ctx.h, stream)

@@ -29,8 +29,10 @@ struct ChanDev {
     // per-stream state / config
     const int8_t* frames;            // [stream][slot][frame_bits]
     size_t stream_frames_stride;     // slots*frame_bits
-    const uint32_t* frames_written;  // [stream]
+    const uint32_t* frames_written;  // [stream] SNAPSHOT of the OFDM stage's counter, taken on the main stream before the channel
+                                     // stream forks: the next OFDM stage advances the live counter while this decode runs
     uint32_t* frames_decoded;        // [stream]
+    uint32_t max_lag;                // frames_written - frames_decoded above this: the history of the oldest frame is overwritten
     const SubCfgDev* subcfg;         // [stream][max_subs]
     const uint32_t* n_subs;          // [stream]
     uint32_t* cifs_consumed;         // [stream][max_subs]
@@ -44,7 +46,22 @@ struct ChanDev {
 };
 
 enum { CNT_FRAMES_DEMOD = 0, CNT_FRAMES_CHAN, CNT_FIB_OK, CNT_FIB_TOTAL, CNT_MSC_BYTES, CNT_SF_OK, CNT_SF_RS_FAIL,
-       CNT_SF_FIRE_FAIL, CNT_AU_OK, CNT_AU_CRC_FAIL, CNT_COUNT };
+       CNT_SF_FIRE_FAIL, CNT_AU_OK, CNT_AU_CRC_FAIL, CNT_FRAMES_DROPPED, CNT_COUNT };
+
+// The frame the channel decoder takes next.  Normally the oldest undecoded one.  When the decoder fell so far behind the OFDM
+// stage that the ring slots holding the 16-CIF history of that frame were overwritten (frames_written - frames_decoded >
+// max_lag), it skips to the newest frame and restarts every time de-interleaver of the stream empty, like a fresh
+// CIF_Deinterleaver (cif_deinterleaver.cpp:38-41): stale soft bits are never decoded as valid.  The reference cannot get there
+// (its ThreadedRingBuffer blocks the producer, src/radio_block.cpp:20-44); dropped frames are counted (CNT_FRAMES_DROPPED).
+struct ChanPick { uint32_t t; bool has_frame, skipped; };
+__device__ __forceinline__ ChanPick chan_pick_frame(const ChanDev& C, const uint32_t s) {
+    ChanPick p;
+    const uint32_t w = C.frames_written[s], d = C.frames_decoded[s];
+    p.has_frame = w > d;
+    p.skipped = p.has_frame && (w - d) > C.max_lag;
+    p.t = p.skipped ? w - 1u : d;
+    return p;
+}
 
 // One thread per potential job: (stream, j).  j < nb_cifs => FIB group j; otherwise sub-channel x CIF.
 // count_plan (optional): the histogram of trellis lengths that k_vit_plan needs is taken here, where the lengths are at hand,
@@ -57,8 +74,9 @@ __global__ void k_chan_build_jobs(const ChanDev C, VitJobDev* __restrict__ jobs,
     const uint32_t s = uint32_t(first_stream) + si;
     VitJobDev J;
     memset(&J, 0, sizeof(J));
-    const uint32_t t = C.frames_decoded[s];
-    const bool has_frame = C.frames_written[s] > t;
+    const ChanPick pick = chan_pick_frame(C, s);
+    const uint32_t t = pick.t;
+    const bool has_frame = pick.has_frame;
     const uint32_t nb_cifs = C.geom.nb_cifs;
     if (j == 0) {
         C.status[2 * s + 0] = has_frame ? 1 : 0;
@@ -86,8 +104,8 @@ __global__ void k_chan_build_jobs(const ChanDev C, VitJobDev* __restrict__ jobs,
             if (sub < C.n_subs[s]) {
                 const SubCfgDev cfg = C.subcfg[size_t(s) * C.max_subs + sub];
                 // CIF_Deinterleaver::Deinterleave returns false until 16 CIFs were consumed (cif_deinterleaver.cpp:38-41)
-                const uint32_t consumed = C.cifs_consumed[size_t(s) * C.max_subs + sub] + c + 1u;
-                const bool valid = consumed >= 16u;
+                const uint32_t consumed = (pick.skipped ? 0u : C.cifs_consumed[size_t(s) * C.max_subs + sub]) + c + 1u;
+                const bool valid = consumed >= 16u && cfg.total_steps != 0u;   // total_steps 0: entry removed (dabgpu_msc_remove_subchannel)
                 C.msc_valid[(size_t(s) * nb_cifs + c) * C.max_subs + sub] = valid ? 1 : 0;
                 if (valid) {
                     J.src = ring;
@@ -117,6 +135,7 @@ __global__ void __launch_bounds__(32) k_chan_finish(const ChanDev C, const int f
     if (si >= uint32_t(n_streams)) return;
     const uint32_t s = uint32_t(first_stream) + si;
     if (!C.status[2 * s]) return;
+    const ChanPick pick = chan_pick_frame(C, s);   // same inputs as in k_chan_build_jobs: frames_decoded only changes below
     const uint32_t nb_cifs = C.geom.nb_cifs;
     unsigned long long bytes = 0;
     const uint32_t ns = C.n_subs[s];
@@ -125,7 +144,7 @@ __global__ void __launch_bounds__(32) k_chan_finish(const ChanDev C, const int f
         const uint32_t nb = C.subcfg[size_t(s) * C.max_subs + sub].n_out_bytes;
         for (uint32_t c = 0; c < nb_cifs; c++)
             if (C.msc_valid[(size_t(s) * nb_cifs + c) * C.max_subs + sub]) bytes += nb;
-        cc = min(cc + nb_cifs, 1u << 30);
+        cc = min((pick.skipped ? 0u : cc) + nb_cifs, 1u << 30);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(FULL_MASK, bytes, o);
@@ -139,6 +158,7 @@ __global__ void __launch_bounds__(32) k_chan_finish(const ChanDev C, const int f
         }
         atomicAdd(&C.counters[CNT_MSC_BYTES], bytes);
         atomicAdd(&C.counters[CNT_FRAMES_CHAN], 1ull);
-        C.frames_decoded[s] += 1u;
+        if (pick.skipped) atomicAdd(&C.counters[CNT_FRAMES_DROPPED], (unsigned long long)(pick.t - C.frames_decoded[s]));
+        C.frames_decoded[s] = pick.t + 1u;
     }
 }

@@ -8,6 +8,7 @@
 #include "ofdm_host.cuh"
 #include "../host/fic_autoconfig.hpp"
 #include "../host/capture_formats.hpp"
+#include <algorithm>
 
 #define DABGPU_VERSION "dabgpu 0.1 (sm_100a)"
 
@@ -15,6 +16,7 @@ struct SubHost {
     dabgpu_subchannel sc;
     Schedule sched;
     uint32_t n_out_bytes, out_offset;
+    bool active = true;   // false: removed by dabgpu_msc_remove_subchannel (the index stays reserved so that the others keep theirs)
 };
 
 struct dabgpu_ctx {
@@ -45,12 +47,14 @@ struct dabgpu_ctx {
 
     // soft-bit frame ring + channel decode state
     DevBuf d_frames, d_frames_written, d_frames_decoded, d_frame_info;
+    DevBuf d_frames_snapshot;   // frames_written as the channel decode sees it (copied on the main stream before the fork)
     DevBuf d_subcfg, d_nsubs, d_cifs_consumed;
     DevBuf d_fic_out, d_fic_crc, d_msc_out, d_msc_valid, d_status, d_counters;
     std::vector<std::vector<SubHost>> subs;
     ChanDev chan;
     PinnedBuf h_status, h_stage;
     std::vector<uint32_t> h_frames_popped;   // per stream, host side cursor of dabgpu_ofdm_pop_frames
+    std::vector<uint32_t> h_frames_dropped;  // per stream, frames dabgpu_ofdm_pop_frames could not deliver (overwritten in the ring)
 
     // DAB+ superframe stage
     DabPlusState dabplus;
@@ -167,7 +171,8 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
     int min_slots = 8;
     // the time de-interleaver needs 16 CIFs of history plus the frame being written
     while (min_slots * P.nb_cifs < 16 + 2 * P.nb_cifs) min_slots *= 2;
-    ctx->frame_slots = cfg->frame_slots > 0 ? cfg->frame_slots : min_slots;
+    // default: twice the minimum, so that a consumer may fall several frames behind the OFDM stage before frames are dropped
+    ctx->frame_slots = cfg->frame_slots > 0 ? cfg->frame_slots : 2 * min_slots;
     if (!is_pow2(size_t(ctx->frame_slots)) || ctx->frame_slots < min_slots) {
         delete ctx;
         return set_error(DABGPU_ERR_INVALID, "frame_slots must be a power of two >= %d", min_slots);
@@ -210,6 +215,7 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
     TRY_OR_FREE(ctx->d_frames.alloc(size_t(S) * ctx->frame_slots * frame_bits));
     TRY_OR_FREE(ctx->d_frames_written.alloc(size_t(S) * 4));
     TRY_OR_FREE(ctx->d_frames_decoded.alloc(size_t(S) * 4));
+    TRY_OR_FREE(ctx->d_frames_snapshot.alloc(size_t(S) * 4));
     TRY_OR_FREE(ctx->d_frame_info.alloc(size_t(S) * ctx->frame_slots * sizeof(dabgpu_frame_info)));
     TRY_OR_FREE(ctx->d_subcfg.alloc(size_t(S) * ctx->max_subs * sizeof(SubCfgDev)));
     TRY_OR_FREE(ctx->d_nsubs.alloc(size_t(S) * 4));
@@ -224,6 +230,7 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
     cudaMemset(ctx->d_frames.p, 0, ctx->d_frames.bytes);
     cudaMemset(ctx->d_frames_written.p, 0, ctx->d_frames_written.bytes);
     cudaMemset(ctx->d_frames_decoded.p, 0, ctx->d_frames_decoded.bytes);
+    cudaMemset(ctx->d_frames_snapshot.p, 0, ctx->d_frames_snapshot.bytes);
     cudaMemset(ctx->d_frame_info.p, 0, ctx->d_frame_info.bytes);
     cudaMemset(ctx->d_subcfg.p, 0, ctx->d_subcfg.bytes);
     cudaMemset(ctx->d_nsubs.p, 0, ctx->d_nsubs.bytes);
@@ -236,6 +243,7 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
     cudaMemset(ctx->d_counters.p, 0, ctx->d_counters.bytes);
     ctx->subs.resize(size_t(S));
     ctx->h_frames_popped.assign(size_t(S), 0);
+    ctx->h_frames_dropped.assign(size_t(S), 0);
 
     ChanDev& C = ctx->chan;
     C.geom.nb_cifs = uint32_t(P.nb_cifs);
@@ -252,7 +260,7 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
     C.jobs_per_stream = uint32_t(P.nb_cifs) * (1u + uint32_t(ctx->max_subs));
     C.frames = ctx->d_frames.as<int8_t>();
     C.stream_frames_stride = size_t(ctx->frame_slots) * frame_bits;
-    C.frames_written = ctx->d_frames_written.as<uint32_t>();
+    C.frames_written = ctx->d_frames_snapshot.as<uint32_t>();
     C.frames_decoded = ctx->d_frames_decoded.as<uint32_t>();
     C.subcfg = ctx->d_subcfg.as<SubCfgDev>();
     C.n_subs = ctx->d_nsubs.as<uint32_t>();
@@ -272,6 +280,15 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
             dabgpu_ctx_destroy(ctx);
             return rc;
         }
+    }
+    {
+        // Decoding frame t gathers CIFs newest-15 .. newest, i.e. the frames t-hist .. t; the newest written frame w-1 shares a
+        // slot with frame w-1-slots, so the history is intact while w - t <= slots - hist.  When the channel decode runs on its
+        // own stream the next OFDM stage may write up to two more frames meanwhile (dabgpu_ofdm_* joins first when a call can
+        // emit more than that), hence two slots of margin.
+        const int hist = (15 + P.nb_cifs - 1) / P.nb_cifs;
+        const int lag = ctx->frame_slots - hist - (ctx->s_dp ? 2 : 0);
+        C.max_lag = uint32_t(lag < 1 ? 1 : lag);
     }
     ctx->ofdm.prof = &ctx->prof;
     TRY_OR_FREE(ofdm_init(ctx->ofdm, ctx->cfg, P, ctx->frame_slots, ctx->d_frames.as<int8_t>(), ctx->d_frames_written.as<uint32_t>(),
@@ -302,7 +319,7 @@ void dabgpu_ctx_destroy(dabgpu_ctx* ctx) {
     ofdm_destroy(ctx->ofdm);
     dabplus_destroy(ctx->dabplus);
     DevBuf* bufs[] = {&ctx->d_vlplan, &ctx->d_vllist, &ctx->d_vlsym, &ctx->d_vlscratch, &ctx->d_prbs, &ctx->d_counter, &ctx->d_scratch, &ctx->d_jobs, &ctx->d_vsoft, &ctx->d_vout, &ctx->d_verr,
-                      &ctx->d_frames, &ctx->d_frames_written, &ctx->d_frames_decoded, &ctx->d_frame_info, &ctx->d_subcfg, &ctx->d_nsubs,
+                      &ctx->d_frames, &ctx->d_frames_written, &ctx->d_frames_decoded, &ctx->d_frames_snapshot, &ctx->d_frame_info, &ctx->d_subcfg, &ctx->d_nsubs,
                       &ctx->d_cifs_consumed, &ctx->d_fic_out, &ctx->d_fic_crc, &ctx->d_msc_out, &ctx->d_msc_valid, &ctx->d_status,
                       &ctx->d_counters};
     for (DevBuf* b : bufs) b->release();
@@ -464,9 +481,9 @@ int dabgpu_viterbi_decode(dabgpu_ctx* ctx, const dabgpu_viterbi_job* jobs, int n
             J.seg_step_end[k] = steps;
         }
         if (in_base > j.n_soft) return set_error(DABGPU_ERR_INVALID, "job %d: needs %u punctured symbols, only %u given", i, in_base, j.n_soft);
-        if (j.soft_offset + j.n_soft > soft_bytes) return set_error(DABGPU_ERR_INVALID, "job %d: soft range exceeds buffer", i);
+        if (j.soft_offset > soft_bytes || j.n_soft > soft_bytes - j.soft_offset) return set_error(DABGPU_ERR_INVALID, "job %d: soft range exceeds buffer", i);
         if (size_t(j.n_out_bytes) * 8 + 6 > steps) return set_error(DABGPU_ERR_INVALID, "job %d: chainback of %u bytes exceeds %u decoded steps", i, j.n_out_bytes, steps);
-        if (j.out_offset + j.n_out_bytes > out_bytes) return set_error(DABGPU_ERR_INVALID, "job %d: output range exceeds buffer", i);
+        if (j.out_offset > out_bytes || j.n_out_bytes > out_bytes - j.out_offset) return set_error(DABGPU_ERR_INVALID, "job %d: output range exceeds buffer", i);
         if (j.descramble && (j.n_out_bytes + 3) / 4 > ctx->prbs_words) return set_error(DABGPU_ERR_INVALID, "job %d: too long for the PRBS table", i);
         J.n_seg = j.n_seg;
         J.total_steps = steps;
@@ -498,67 +515,144 @@ static int check_stream_range(dabgpu_ctx* ctx, int first, int n) {
     return DABGPU_OK;
 }
 
+// Validates one sub-channel description and builds its host / device records (out_offset is assigned by the caller).
+static int build_sub(dabgpu_ctx* ctx, const dabgpu_subchannel& sc, int index, SubHost* h, SubCfgDev* d) {
+    h->sc = sc;
+    h->active = true;
+    if (sc.start_address < 0 || sc.length <= 0 || (sc.start_address + sc.length) * 64 > ctx->P.nb_cif_bits)
+        return set_error(DABGPU_ERR_INVALID, "Subchannel bits %d:%d overflows MSC channel with %d bits", sc.start_address * 64,
+                         (sc.start_address + sc.length) * 64, ctx->P.nb_cif_bits);
+    int rc;
+    if ((rc = make_schedule(sc, &h->sched))) return rc;
+    const int steps = h->sched.total_steps();
+    if (h->sched.punctured_bits() > sc.length * 64)
+        return set_error(DABGPU_ERR_INVALID, "sub-channel %d: protection profile needs %d soft bits, sub-channel has %d", index, h->sched.punctured_bits(), sc.length * 64);
+    h->n_out_bytes = uint32_t((steps - 6) / 8);
+    h->out_offset = 0;
+    memset(d, 0, sizeof(*d));
+    d->start_bit = uint32_t(sc.start_address * 64);
+    d->nb_bits = uint32_t(sc.length * 64);
+    uint32_t st = 0, inb = 0;
+    for (int k = 0; k < DABGPU_MAX_SEGMENTS; k++) {
+        if (k < h->sched.n_seg) {
+            d->seg_pi[k] = uint8_t(h->sched.pi[k]);
+            d->seg_in_base[k] = inb;
+            int c[8];
+            host_pi_counts(h->sched.pi[k], c);
+            const uint32_t groups = uint32_t(h->sched.bits[k] / 4);
+            uint32_t per8 = 0;
+            for (int g = 0; g < 8; g++) per8 += uint32_t(c[g]);
+            inb += (groups / 8) * per8;
+            for (uint32_t g = 0; g < groups % 8; g++) inb += uint32_t(c[g]);
+            st += groups;
+        }
+        d->seg_step_end[k] = st;
+    }
+    d->n_seg = uint32_t(h->sched.n_seg);
+    d->total_steps = uint32_t(steps);
+    d->n_out_bytes = h->n_out_bytes;
+    d->is_dabplus = sc.is_dabplus ? 1u : 0u;
+    return DABGPU_OK;
+}
+
+static bool same_subchannel(const dabgpu_subchannel& a, const dabgpu_subchannel& b) {
+    if (a.start_address != b.start_address || a.length != b.length || (a.is_uep != 0) != (b.is_uep != 0) || (a.is_dabplus != 0) != (b.is_dabplus != 0)) return false;
+    return a.is_uep ? (a.uep_prot_index == b.uep_prot_index) : (a.eep_prot_level == b.eep_prot_level && (a.eep_type_b != 0) == (b.eep_type_b != 0));
+}
+
+// Writes entry `index` of a stream's sub-channel table to the device; `fresh` also empties its time de-interleaver and DAB+
+// superframe state (a new MSC_Decoder + AAC_Frame_Processor), otherwise the running state is left alone.
+static int upload_sub(dabgpu_ctx* ctx, int stream, int index, const SubCfgDev& d, bool fresh) {
+    const size_t idx = size_t(stream) * ctx->max_subs + size_t(index);
+    CUDA_TRY(cudaMemcpy(ctx->d_subcfg.as<SubCfgDev>() + idx, &d, sizeof(SubCfgDev), cudaMemcpyHostToDevice));
+    if (fresh) {
+        CUDA_TRY(cudaMemset(ctx->d_cifs_consumed.as<uint32_t>() + idx, 0, 4));
+        CUDA_TRY(cudaMemset(ctx->dabplus.dev.st + idx, 0, sizeof(DabPlusSubState)));
+        CUDA_TRY(cudaMemset(ctx->dabplus.dev.n_events + idx, 0, 4));
+    }
+    return DABGPU_OK;
+}
+
+static int upload_nsubs(dabgpu_ctx* ctx, int stream, size_t n) {
+    const uint32_t ns = uint32_t(n);
+    CUDA_TRY(cudaMemcpy(ctx->d_nsubs.as<uint32_t>() + stream, &ns, 4, cudaMemcpyHostToDevice));
+    ctx->cfg_epoch++;
+    return DABGPU_OK;
+}
+
+// BasicRadio keeps the decoders it already has when the database grows (basic_radio.cpp:98-131): entries of the new table that
+// are identical to the entry at the same index of the old one -- same description, same place in the output arena -- keep their
+// time de-interleaver and superframe state; every other entry starts empty like a new MSC_Decoder.
 int dabgpu_msc_configure(dabgpu_ctx* ctx, int stream, const dabgpu_subchannel* subs, int n_subs) {
     int rc = check_stream_range(ctx, stream, 1);
     if (rc) return rc;
     if (n_subs < 0 || n_subs > ctx->max_subs) return set_error(DABGPU_ERR_INVALID, "n_subs %d exceeds max_subchannels %d", n_subs, ctx->max_subs);
     if (n_subs > 0 && !subs) return set_error(DABGPU_ERR_INVALID, "null sub-channel table");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
-    std::vector<SubHost> hs;
-    std::vector<SubCfgDev> dev(static_cast<size_t>(ctx->max_subs));
-    memset(dev.data(), 0, dev.size() * sizeof(SubCfgDev));
+    std::vector<SubHost> hs(static_cast<size_t>(n_subs));
+    std::vector<SubCfgDev> dev(static_cast<size_t>(n_subs));
     uint32_t out_off = 0, max_steps = 0;
     for (int i = 0; i < n_subs; i++) {
-        SubHost h;
-        h.sc = subs[i];
-        if (h.sc.start_address < 0 || h.sc.length <= 0 || (h.sc.start_address + h.sc.length) * 64 > ctx->P.nb_cif_bits)
-            return set_error(DABGPU_ERR_INVALID, "Subchannel bits %d:%d overflows MSC channel with %d bits", h.sc.start_address * 64,
-                             (h.sc.start_address + h.sc.length) * 64, ctx->P.nb_cif_bits);
-        if ((rc = make_schedule(h.sc, &h.sched))) return rc;
-        const int steps = h.sched.total_steps();
-        if (h.sched.punctured_bits() > h.sc.length * 64)
-            return set_error(DABGPU_ERR_INVALID, "sub-channel %d: protection profile needs %d soft bits, sub-channel has %d", i, h.sched.punctured_bits(), h.sc.length * 64);
-        h.n_out_bytes = uint32_t((steps - 6) / 8);
-        h.out_offset = out_off;
-        out_off += (h.n_out_bytes + 15u) & ~15u;
+        if ((rc = build_sub(ctx, subs[i], i, &hs[size_t(i)], &dev[size_t(i)]))) return rc;
+        hs[size_t(i)].out_offset = dev[size_t(i)].out_offset = out_off;
+        out_off += (hs[size_t(i)].n_out_bytes + 15u) & ~15u;
         if (out_off > CIF_OUT_STRIDE) return set_error(DABGPU_ERR_OVERFLOW, "decoded bytes per CIF exceed %u", CIF_OUT_STRIDE);
-        SubCfgDev& d = dev[size_t(i)];
-        d.start_bit = uint32_t(h.sc.start_address * 64);
-        d.nb_bits = uint32_t(h.sc.length * 64);
-        uint32_t st = 0, inb = 0;
-        for (int k = 0; k < DABGPU_MAX_SEGMENTS; k++) {
-            if (k < h.sched.n_seg) {
-                d.seg_pi[k] = uint8_t(h.sched.pi[k]);
-                d.seg_in_base[k] = inb;
-                int c[8];
-                host_pi_counts(h.sched.pi[k], c);
-                const uint32_t groups = uint32_t(h.sched.bits[k] / 4);
-                uint32_t per8 = 0;
-                for (int g = 0; g < 8; g++) per8 += uint32_t(c[g]);
-                inb += (groups / 8) * per8;
-                for (uint32_t g = 0; g < groups % 8; g++) inb += uint32_t(c[g]);
-                st += groups;
-            }
-            d.seg_step_end[k] = st;
-        }
-        d.n_seg = uint32_t(h.sched.n_seg);
-        d.total_steps = uint32_t(steps);
-        d.n_out_bytes = h.n_out_bytes;
-        d.out_offset = h.out_offset;
-        d.is_dabplus = h.sc.is_dabplus ? 1u : 0u;
-        if (d.total_steps > max_steps) max_steps = d.total_steps;
-        hs.push_back(h);
+        max_steps = std::max(max_steps, dev[size_t(i)].total_steps);
     }
     if ((rc = ensure_scratch(ctx, max_steps))) return rc;
     CUDA_TRY(sync_ctx(ctx));
-    CUDA_TRY(cudaMemcpy(ctx->d_subcfg.as<SubCfgDev>() + size_t(stream) * ctx->max_subs, dev.data(), dev.size() * sizeof(SubCfgDev), cudaMemcpyHostToDevice));
-    const uint32_t ns = uint32_t(n_subs);
-    CUDA_TRY(cudaMemcpy(ctx->d_nsubs.as<uint32_t>() + stream, &ns, 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemset(ctx->d_cifs_consumed.as<uint32_t>() + size_t(stream) * ctx->max_subs, 0, size_t(ctx->max_subs) * 4));
-    if ((rc = dabplus_reset_stream(ctx->dabplus, stream))) return rc;
+    const std::vector<SubHost>& old = ctx->subs[size_t(stream)];
+    for (int i = 0; i < n_subs; i++) {
+        const bool keep = size_t(i) < old.size() && old[size_t(i)].active && old[size_t(i)].out_offset == hs[size_t(i)].out_offset &&
+                          same_subchannel(old[size_t(i)].sc, hs[size_t(i)].sc);
+        if ((rc = upload_sub(ctx, stream, i, dev[size_t(i)], !keep))) return rc;
+    }
     ctx->subs[size_t(stream)] = hs;
-    ctx->cfg_epoch++;
-    return DABGPU_OK;
+    return upload_nsubs(ctx, stream, hs.size());
+}
+
+// Attaches a decoder to one more sub-channel of a stream without touching the running ones (BasicRadio::UpdateAfterProcessing,
+// basic_radio.cpp:98-131).  *sub_index_out = its index for dabgpu_chan_get_msc / _get_dabplus_events / dabgpu_msc_get_layout.
+int dabgpu_msc_add_subchannel(dabgpu_ctx* ctx, int stream, const dabgpu_subchannel* sub, int* sub_index_out) {
+    int rc = check_stream_range(ctx, stream, 1);
+    if (rc) return rc;
+    if (!sub) return set_error(DABGPU_ERR_INVALID, "null sub-channel");
+    std::vector<SubHost>& hs = ctx->subs[size_t(stream)];
+    if (int(hs.size()) >= ctx->max_subs) return set_error(DABGPU_ERR_OVERFLOW, "sub-channel table of stream %d is full (%d entries)", stream, ctx->max_subs);
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    SubHost h;
+    SubCfgDev d;
+    if ((rc = build_sub(ctx, *sub, int(hs.size()), &h, &d))) return rc;
+    uint32_t out_off = 0;
+    for (const SubHost& o : hs) out_off = std::max(out_off, o.out_offset + ((o.n_out_bytes + 15u) & ~15u));
+    if (out_off + h.n_out_bytes > CIF_OUT_STRIDE) return set_error(DABGPU_ERR_OVERFLOW, "decoded bytes per CIF exceed %u", CIF_OUT_STRIDE);
+    h.out_offset = d.out_offset = out_off;
+    if ((rc = ensure_scratch(ctx, d.total_steps))) return rc;
+    CUDA_TRY(sync_ctx(ctx));
+    if ((rc = upload_sub(ctx, stream, int(hs.size()), d, true))) return rc;
+    hs.push_back(h);
+    if (sub_index_out) *sub_index_out = int(hs.size()) - 1;
+    return upload_nsubs(ctx, stream, hs.size());
+}
+
+// Detaches the decoder of one sub-channel; the indices of the others do not change (the slot stays reserved until a
+// dabgpu_msc_configure).  The reference never removes a decoder; this exists for hosts that retune a service.
+int dabgpu_msc_remove_subchannel(dabgpu_ctx* ctx, int stream, int sub_index) {
+    int rc = check_stream_range(ctx, stream, 1);
+    if (rc) return rc;
+    std::vector<SubHost>& hs = ctx->subs[size_t(stream)];
+    if (sub_index < 0 || size_t(sub_index) >= hs.size() || !hs[size_t(sub_index)].active) return set_error(DABGPU_ERR_INVALID, "sub-channel index %d not configured", sub_index);
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(sync_ctx(ctx));
+    SubCfgDev d;
+    memset(&d, 0, sizeof(d));   // total_steps = 0: k_chan_build_jobs emits no job and marks every CIF invalid
+    d.out_offset = hs[size_t(sub_index)].out_offset;
+    if ((rc = upload_sub(ctx, stream, sub_index, d, true))) return rc;
+    hs[size_t(sub_index)].active = false;
+    const size_t nb_cifs = size_t(ctx->P.nb_cifs);
+    for (size_t c = 0; c < nb_cifs; c++)
+        CUDA_TRY(cudaMemset(ctx->d_msc_valid.as<uint8_t>() + (size_t(stream) * nb_cifs + c) * ctx->max_subs + size_t(sub_index), 0, 1));
+    return upload_nsubs(ctx, stream, hs.size());
 }
 
 int dabgpu_softbits_push(dabgpu_ctx* ctx, const int8_t* frames_host, size_t stride, int first, int n) {
@@ -568,10 +662,18 @@ int dabgpu_softbits_push(dabgpu_ctx* ctx, const int8_t* frames_host, size_t stri
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     // BasicRadio::Process requires exactly nb_frame_bits per call (basic_radio.cpp:41-46): the caller passes whole frames
     const size_t fb = size_t(ctx->P.nb_frame_bits);
-    if ((rc = ctx->h_stage.alloc(size_t(n) * 4 + 64))) return rc;
     CUDA_TRY(sync_ctx(ctx));
+    if ((rc = ctx->h_stage.alloc(size_t(n) * 8 + 64))) return rc;
     uint32_t* written = ctx->h_stage.as<uint32_t>();
+    uint32_t* decoded = written + n;
     CUDA_TRY(cudaMemcpy(written, ctx->d_frames_written.as<uint32_t>() + first, size_t(n) * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(decoded, ctx->d_frames_decoded.as<uint32_t>() + first, size_t(n) * 4, cudaMemcpyDeviceToHost));
+    // the ring is full when one more frame would overwrite the history of the oldest undecoded one (the reference's
+    // ThreadedRingBuffer blocks its producer there, src/radio_block.cpp:20-44): refuse instead of corrupting it
+    for (int i = 0; i < n; i++)
+        if (written[i] - decoded[i] >= ctx->chan.max_lag)
+            return set_error(DABGPU_ERR_OVERFLOW, "soft-bit frame ring of stream %d is full (%u frames not channel-decoded yet): call dabgpu_chan_decode", first + i,
+                             written[i] - decoded[i]);
     for (int i = 0; i < n; i++) {
         const size_t slot = written[i] & uint32_t(ctx->frame_slots - 1);
         int8_t* dst = ctx->d_frames.as<int8_t>() + (size_t(first + i) * ctx->frame_slots + slot) * fb;
@@ -614,8 +716,8 @@ int dabgpu_bytes_to_softbits(const uint8_t* bytes, size_t n_bytes, int8_t* bits)
 // ---------------------------------------------------------------------------------------------
 struct dabgpu_autocfg {
     dabgpu_host::FIC_Autoconfig db;
-    std::vector<dabgpu_subchannel> applied;
-    bool applied_once = false;
+    std::vector<uint8_t> applied_ids;    // SubChIds that got a decoder, in sub_index order
+    std::vector<uint8_t> rejected_ids;   // complete in the database but not decodable (bad range / protection profile): never retried
 };
 
 dabgpu_autocfg* dabgpu_autocfg_create(void) { return new dabgpu_autocfg(); }
@@ -667,17 +769,36 @@ int dabgpu_autocfg_runnable(dabgpu_autocfg* a, dabgpu_subchannel* out, uint8_t* 
     return DABGPU_OK;
 }
 
+// BasicRadio::UpdateAfterProcessing (basic_radio.cpp:83-154): every sub-channel that became runnable since the last call gets a
+// decoder (dabgpu_msc_add_subchannel); the running ones are not touched.  A sub-channel the context refuses (range or
+// protection profile invalid) is remembered and skipped: in the reference a bad sub-channel only affects itself.
+// One dabgpu_autocfg object serves one (context, stream) pair whose table it fills alone.
 int dabgpu_autocfg_apply(dabgpu_autocfg* a, dabgpu_ctx* ctx, int stream) {
     if (!a || !ctx) return set_error(DABGPU_ERR_INVALID, "null argument");
     std::vector<dabgpu_subchannel> v;
     std::vector<uint8_t> id;
     a->db.Runnable(v, id);
-    if (a->applied_once && v.size() == a->applied.size() && (v.empty() || memcmp(v.data(), a->applied.data(), v.size() * sizeof(dabgpu_subchannel)) == 0)) return 0;
-    const int rc = dabgpu_msc_configure(ctx, stream, v.data(), int(v.size()));
-    if (rc) return rc;
-    a->applied = v;
-    a->applied_once = true;
-    return 1;
+    int added = 0;
+    for (size_t i = 0; i < v.size(); i++) {
+        if (std::find(a->applied_ids.begin(), a->applied_ids.end(), id[i]) != a->applied_ids.end()) continue;
+        if (std::find(a->rejected_ids.begin(), a->rejected_ids.end(), id[i]) != a->rejected_ids.end()) continue;
+        const int rc = dabgpu_msc_add_subchannel(ctx, stream, &v[i], nullptr);
+        if (rc == DABGPU_ERR_INVALID || rc == DABGPU_ERR_OVERFLOW) { a->rejected_ids.push_back(id[i]); continue; }
+        if (rc) return rc;
+        a->applied_ids.push_back(id[i]);
+        added++;
+    }
+    return added > 0 ? 1 : 0;
+}
+
+int dabgpu_autocfg_applied(dabgpu_autocfg* a, uint8_t* ids, int cap, int* n_out) {
+    if (!a || !n_out) return set_error(DABGPU_ERR_INVALID, "null argument");
+    *n_out = int(a->applied_ids.size());
+    if (ids) {
+        if (cap < *n_out) return set_error(DABGPU_ERR_OVERFLOW, "%d applied sub-channels, room for %d", *n_out, cap);
+        memcpy(ids, a->applied_ids.data(), a->applied_ids.size());
+    }
+    return DABGPU_OK;
 }
 
 // The kernels of one channel decode, all on ctx->stream (which dabgpu_chan_decode points at the channel stream meanwhile).
@@ -695,7 +816,7 @@ static int chan_decode_body(dabgpu_ctx* ctx, int first, int n) {
         VlBound vb;
         for (int s = first; s < first + n; s++) {
             if (ctx->chan.fic_enabled) vb.add(774u, uint32_t(ctx->P.nb_cifs));
-            for (const SubHost& h : ctx->subs[size_t(s)]) vb.add(uint32_t(h.sched.total_steps()), uint32_t(ctx->P.nb_cifs));
+            for (const SubHost& h : ctx->subs[size_t(s)]) if (h.active) vb.add(uint32_t(h.sched.total_steps()), uint32_t(ctx->P.nb_cifs));
         }
         memcpy(ctx->vl_cache.count, vb.count, sizeof(vb.count));
         ctx->vl_cache.max_steps = vb.max_steps;
@@ -732,6 +853,10 @@ int dabgpu_chan_decode(dabgpu_ctx* ctx, int first, int n) {
     CUDA_TRY(join_dabplus(ctx));
     const bool fork = ctx->s_dp != nullptr && !ctx->prof.on;
     cudaStream_t main_stream = ctx->stream;
+    // what the OFDM stage (or dabgpu_softbits_push) has produced so far; the decode kernels only read this copy, because the
+    // next OFDM stage advances the live counters on the main stream while the decode runs on the channel stream
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_frames_snapshot.as<uint32_t>() + first, ctx->d_frames_written.as<uint32_t>() + first, size_t(n) * 4,
+                             cudaMemcpyDeviceToDevice, main_stream));
     if (fork) {
         CUDA_TRY(cudaEventRecord(ctx->ev_dp_fork, main_stream));
         CUDA_TRY(cudaStreamWaitEvent(ctx->s_dp, ctx->ev_dp_fork, 0));
@@ -743,6 +868,14 @@ int dabgpu_chan_decode(dabgpu_ctx* ctx, int first, int n) {
         if (cudaEventRecord(ctx->ev_dp, ctx->s_dp) == cudaSuccess) ctx->dp_pending = true;
     }
     return rc;
+}
+
+// Non-blocking: everything queued on the context's stream after this call waits for the last dabgpu_chan_decode.
+int dabgpu_chan_join(dabgpu_ctx* ctx) {
+    if (!ctx) return set_error(DABGPU_ERR_INVALID, "null context");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(join_dabplus(ctx));
+    return DABGPU_OK;
 }
 
 int dabgpu_chan_get_status(dabgpu_ctx* ctx, int stream, dabgpu_chan_status* out) {
@@ -777,7 +910,7 @@ int dabgpu_chan_get_msc(dabgpu_ctx* ctx, int stream, int sub_index, uint8_t* out
     int rc = check_stream_range(ctx, stream, 1);
     if (rc) return rc;
     const auto& hs = ctx->subs[size_t(stream)];
-    if (sub_index < 0 || size_t(sub_index) >= hs.size()) return set_error(DABGPU_ERR_INVALID, "sub-channel index %d not configured", sub_index);
+    if (sub_index < 0 || size_t(sub_index) >= hs.size() || !hs[size_t(sub_index)].active) return set_error(DABGPU_ERR_INVALID, "sub-channel index %d not configured", sub_index);
     const SubHost& h = hs[size_t(sub_index)];
     const int nb_cifs = ctx->P.nb_cifs;
     if (bytes_per_cif) *bytes_per_cif = int(h.n_out_bytes);
@@ -799,7 +932,8 @@ int dabgpu_chan_get_msc(dabgpu_ctx* ctx, int stream, int sub_index, uint8_t* out
 int dabgpu_chan_get_dabplus_events(dabgpu_ctx* ctx, int stream, int sub_index, uint8_t* log_host, size_t log_cap, size_t* log_bytes) {
     int rc = check_stream_range(ctx, stream, 1);
     if (rc) return rc;
-    if (sub_index < 0 || size_t(sub_index) >= ctx->subs[size_t(stream)].size()) return set_error(DABGPU_ERR_INVALID, "sub-channel index %d not configured", sub_index);
+    if (sub_index < 0 || size_t(sub_index) >= ctx->subs[size_t(stream)].size() || !ctx->subs[size_t(stream)][size_t(sub_index)].active)
+        return set_error(DABGPU_ERR_INVALID, "sub-channel index %d not configured", sub_index);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     CUDA_TRY(sync_ctx(ctx));
     return dabplus_get_events(ctx->dabplus, stream, sub_index, log_host, log_cap, log_bytes);
@@ -924,6 +1058,7 @@ int dabgpu_get_counters(dabgpu_ctx* ctx, dabgpu_counters* out) {
     out->superframes_firecode_fail = c[CNT_SF_FIRE_FAIL];
     out->au_ok = c[CNT_AU_OK];
     out->au_crc_fail = c[CNT_AU_CRC_FAIL];
+    out->frames_dropped = c[CNT_FRAMES_DROPPED];
     return DABGPU_OK;
 }
 
@@ -945,11 +1080,19 @@ int dabgpu_ofdm_reset(dabgpu_ctx* ctx, int stream) {
     return ofdm_reset(ctx->ofdm, stream, ctx->stream);
 }
 
+// A channel decode that is still running on the channel stream reads frame-ring slots that the OFDM stage may overwrite once it
+// emits more than two further frames (ChanDev.max_lag keeps two slots of margin): such calls wait for the decode first.
+static cudaError_t join_if_many_frames(dabgpu_ctx* ctx, long n_samples) {
+    const long max_frames = n_samples / long(ctx->P.nb_frame_samples - ctx->P.nb_cyclic_prefix) + 1;
+    return (ctx->dp_pending && max_frames > 2) ? join_dabplus(ctx) : cudaSuccess;
+}
+
 int dabgpu_ofdm_process(dabgpu_ctx* ctx, const void* iq_host, size_t stride_bytes, int first, int n, int n_samples, int block_size) {
     int rc = check_stream_range(ctx, first, n);
     if (rc) return rc;
     if (!iq_host || n_samples < 0) return set_error(DABGPU_ERR_INVALID, "bad IQ buffer");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(join_if_many_frames(ctx, n_samples));
     return ofdm_process(ctx->ofdm, iq_host, stride_bytes, first, n, n_samples, block_size, ctx->stream);
 }
 
@@ -963,6 +1106,7 @@ int dabgpu_ofdm_advance(dabgpu_ctx* ctx, int first, int n, int n_samples, int bl
     int rc = check_stream_range(ctx, first, n);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(join_if_many_frames(ctx, n_samples));
     return ofdm_advance(ctx->ofdm, first, n, n_samples, block_size, ctx->stream);
 }
 
@@ -979,6 +1123,18 @@ int dabgpu_ofdm_get_response(dabgpu_ctx* ctx, int stream, int kind, float* out, 
     return DABGPU_OK;
 }
 
+int dabgpu_ofdm_get_correlation_buffer(dabgpu_ctx* ctx, int stream, float* out, size_t n_floats) {
+    int rc = check_stream_range(ctx, stream, 1);
+    if (rc) return rc;
+    if (!out) return set_error(DABGPU_ERR_INVALID, "null output");
+    const size_t n = size_t(ctx->P.nb_null_period + ctx->P.nb_symbol_period);
+    if (n_floats < 2 * n) return set_error(DABGPU_ERR_OVERFLOW, "correlation buffer needs %zu floats", 2 * n);
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpy(out, ctx->ofdm.dev.corr + size_t(stream) * n, n * sizeof(float2), cudaMemcpyDeviceToHost));
+    return DABGPU_OK;
+}
+
 int dabgpu_ofdm_get_frame_fft(dabgpu_ctx* ctx, int stream, float* out, size_t n_floats) {
     int rc = check_stream_range(ctx, stream, 1);
     if (rc) return rc;
@@ -986,7 +1142,21 @@ int dabgpu_ofdm_get_frame_fft(dabgpu_ctx* ctx, int stream, float* out, size_t n_
     const size_t need = size_t(ctx->P.nb_frame_symbols) * size_t(ctx->P.nb_fft) * 2;
     if (n_floats < need) return set_error(DABGPU_ERR_OVERFLOW, "frame spectrum needs %zu floats", need);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
-    return ofdm_frame_fft(ctx->ofdm, stream, out, ctx->stream);
+    CUDA_TRY(join_dabplus(ctx));
+    // callers that give room for nb_frame_symbols + 1 rows also get the NULL-symbol row, like the reference's buffer
+    const bool with_null = n_floats >= need + size_t(ctx->P.nb_fft) * 2;
+    return ofdm_frame_fft(ctx->ofdm, stream, out, with_null, nullptr, ctx->stream);
+}
+
+int dabgpu_ofdm_get_frame_data_vec(dabgpu_ctx* ctx, int stream, float* out, size_t n_floats) {
+    int rc = check_stream_range(ctx, stream, 1);
+    if (rc) return rc;
+    if (!out) return set_error(DABGPU_ERR_INVALID, "null output");
+    const size_t need = size_t(ctx->P.nb_frame_symbols - 1) * size_t(ctx->P.nb_data_carriers) * 2;
+    if (n_floats < need) return set_error(DABGPU_ERR_OVERFLOW, "frame data vectors need %zu floats", need);
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(join_dabplus(ctx));
+    return ofdm_frame_fft(ctx->ofdm, stream, nullptr, false, out, ctx->stream);
 }
 
 int dabgpu_ofdm_get_status(dabgpu_ctx* ctx, int stream, dabgpu_ofdm_status* out) {
@@ -999,6 +1169,7 @@ int dabgpu_ofdm_get_status(dabgpu_ctx* ctx, int stream, dabgpu_ofdm_status* out)
     uint32_t written = 0;
     CUDA_TRY(cudaMemcpy(&written, ctx->d_frames_written.as<uint32_t>() + stream, 4, cudaMemcpyDeviceToHost));
     out->frames_queued = int(written - ctx->h_frames_popped[size_t(stream)]);
+    out->frames_dropped = int(ctx->h_frames_dropped[size_t(stream)]);
     return DABGPU_OK;
 }
 
@@ -1014,6 +1185,7 @@ int dabgpu_ofdm_pop_frames(dabgpu_ctx* ctx, int stream, int8_t* frames_host, int
     // frames older than the ring depth were overwritten: the observer model of the reference drops nothing, so
     // callers must pop at least every frame_slots-2 frames; report the overrun instead of returning stale data
     if (written - popped > uint32_t(ctx->frame_slots - 1)) {
+        ctx->h_frames_dropped[size_t(stream)] += (written - uint32_t(ctx->frame_slots - 1)) - popped;   // dabgpu_ofdm_status.frames_dropped
         popped = written - uint32_t(ctx->frame_slots - 1);
     }
     const size_t fb = size_t(ctx->P.nb_frame_bits);
@@ -1063,6 +1235,7 @@ int dabgpu_submit(dabgpu_ctx* ctx, const dabgpu_step* st, uint64_t* ticket) {
     if (O.external_ring) return set_error(DABGPU_ERR_STATE, "a device input buffer is attached: use dabgpu_ofdm_advance");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     if ((rc = pipe_init(ctx))) return rc;
+    CUDA_TRY(join_if_many_frames(ctx, st->n_samples));
     const uint64_t t = ctx->next_ticket;
     auto& sl = ctx->pipe[t % DABGPU_PIPELINE_DEPTH];
     auto& prev = ctx->pipe[(t + DABGPU_PIPELINE_DEPTH - 1) % DABGPU_PIPELINE_DEPTH];
@@ -1126,7 +1299,7 @@ int dabgpu_msc_get_layout(dabgpu_ctx* ctx, int stream, int sub_index, int* offse
     int rc = check_stream_range(ctx, stream, 1);
     if (rc) return rc;
     const auto& hs = ctx->subs[size_t(stream)];
-    if (sub_index < 0 || size_t(sub_index) >= hs.size()) return set_error(DABGPU_ERR_INVALID, "sub-channel index %d not configured", sub_index);
+    if (sub_index < 0 || size_t(sub_index) >= hs.size() || !hs[size_t(sub_index)].active) return set_error(DABGPU_ERR_INVALID, "sub-channel index %d not configured", sub_index);
     if (offset) *offset = int(hs[size_t(sub_index)].out_offset);
     if (bytes_per_cif) *bytes_per_cif = int(hs[size_t(sub_index)].n_out_bytes);
     return DABGPU_OK;

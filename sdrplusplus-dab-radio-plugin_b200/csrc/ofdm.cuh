@@ -637,6 +637,8 @@ __global__ void k_ofdm_gather_latest(const OfdmDev D, const int first_stream, in
 // OFDM_Demod::GetFrameFFT (ofdm_demodulator.h:135, filled by PipelineThread, ofdm_demodulator.cpp:673-700): the spectra of the
 // PRS and the data symbols of the last emitted frame, natural bin order, recomputed on demand from the IQ that is still in the
 // ring (the demodulation kernel keeps its spectra in registers).  One CTA per symbol; same PLL and FFT as the control kernel.
+// Row L is the spectrum of the first symbol period of the NULL symbol that follows the frame, like the reference's pipeline
+// computes it (GetDataSymbol(L) of ofdm_frame_buffer.h is the head of the NULL symbol; TII lives there).
 template <int N>
 __global__ void __launch_bounds__(N / 8) k_ofdm_diag_fft(const OfdmDev D, const int s, float2* __restrict__ out) {
     constexpr int NT = N / 8;
@@ -660,6 +662,19 @@ __global__ void __launch_bounds__(N / 8) k_ofdm_diag_fft(const OfdmDev D, const 
         const int i = tid + j * NT;
         const int p = D.dpos[i];
         out[size_t(l) * N + i] = make_float2(a_re[p], a_im[p]);
+    }
+}
+
+// OFDM_Demod::GetFrameDataVec (ofdm_demodulator.h:136; CalculateDQPSK, ofdm_demodulator.cpp:842-865): row i holds
+// X_i[k] * conj(X_{i+1}[k]) for the K data carriers k = -K/2 .. K/2 without 0, before the frequency de-interleaver.
+__global__ void k_ofdm_diag_dqpsk(const float2* __restrict__ spec, float2* __restrict__ out, const int N, const int K) {
+    const int i = blockIdx.x;
+    const float2* x0 = spec + size_t(i) * N;
+    const float2* x1 = x0 + N;
+    for (int c = threadIdx.x; c < K; c += blockDim.x) {
+        const int k = (c < K / 2) ? (c - K / 2) : (c - K / 2 + 1);
+        const float2 a = x0[(N + k) % N], b = x1[(N + k) % N];
+        out[size_t(i) * K + c] = make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
     }
 }
 

@@ -456,27 +456,35 @@ static int ofdm_get_status(OfdmState& O, int stream, dabgpu_ofdm_status* out, cu
     return DABGPU_OK;
 }
 
-// GetFrameFFT tap: L x N complex spectra of the last emitted frame of one stream; DABGPU_ERR_STATE when no frame was emitted yet
-// or the frame was not contiguous in the ring (the first frame after an acquisition)
-static int ofdm_frame_fft(OfdmState& O, int stream, float* host_out, cudaStream_t cs) {
+// GetFrameFFT tap: (L [+1]) x N complex spectra of the last emitted frame of one stream (with_null: plus the NULL-symbol row);
+// GetFrameDataVec tap: (L-1) x K DQPSK vectors of the same frame.  DABGPU_ERR_STATE when no frame was emitted yet or the frame
+// was not contiguous in the ring (the first frame after an acquisition).
+static int ofdm_frame_fft(OfdmState& O, int stream, float* host_fft, bool with_null, float* host_vec, cudaStream_t cs) {
     if (!O.d_diag_meta.p) return set_error(DABGPU_ERR_STATE, "context was created without DABGPU_FLAG_DIAG_TAPS");
-    const int L = O.P.nb_frame_symbols, N = O.P.nb_fft;
+    const int L = O.P.nb_frame_symbols, N = O.P.nb_fft, K = O.P.nb_data_carriers;
     int rc;
-    if ((rc = O.d_diag_fft.alloc(size_t(L) * N * sizeof(float2)))) return rc;
+    if ((rc = O.d_diag_fft.alloc((size_t(L + 1) * N + size_t(L - 1) * K) * sizeof(float2)))) return rc;
     CUDA_TRY(cudaStreamSynchronize(cs));
     OfdmDiagMeta m;
     CUDA_TRY(cudaMemcpy(&m, O.d_diag_meta.as<OfdmDiagMeta>() + stream, sizeof(m), cudaMemcpyDeviceToHost));
     if (!m.valid) return set_error(DABGPU_ERR_STATE, "no frame spectrum available for stream %d yet", stream);
     float2* out = O.d_diag_fft.as<float2>();
+    float2* vec = out + size_t(L + 1) * N;
+    const int rows = L + 1;
     switch (N) {
-    case 2048: k_ofdm_diag_fft<2048><<<L, 256, 0, cs>>>(O.dev, stream, out); break;
-    case 1024: k_ofdm_diag_fft<1024><<<L, 128, 0, cs>>>(O.dev, stream, out); break;
-    case 512: k_ofdm_diag_fft<512><<<L, 64, 0, cs>>>(O.dev, stream, out); break;
-    default: k_ofdm_diag_fft<256><<<L, 32, 0, cs>>>(O.dev, stream, out); break;
+    case 2048: k_ofdm_diag_fft<2048><<<rows, 256, 0, cs>>>(O.dev, stream, out); break;
+    case 1024: k_ofdm_diag_fft<1024><<<rows, 128, 0, cs>>>(O.dev, stream, out); break;
+    case 512: k_ofdm_diag_fft<512><<<rows, 64, 0, cs>>>(O.dev, stream, out); break;
+    default: k_ofdm_diag_fft<256><<<rows, 32, 0, cs>>>(O.dev, stream, out); break;
     }
     O.launches++;
+    if (host_vec) {
+        k_ofdm_diag_dqpsk<<<L - 1, 256, 0, cs>>>(out, vec, N, K);
+        O.launches++;
+    }
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(host_out, out, size_t(L) * N * sizeof(float2), cudaMemcpyDeviceToHost, cs));
+    if (host_fft) CUDA_TRY(cudaMemcpyAsync(host_fft, out, size_t(with_null ? L + 1 : L) * N * sizeof(float2), cudaMemcpyDeviceToHost, cs));
+    if (host_vec) CUDA_TRY(cudaMemcpyAsync(host_vec, vec, size_t(L - 1) * K * sizeof(float2), cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaStreamSynchronize(cs));
     return DABGPU_OK;
 }

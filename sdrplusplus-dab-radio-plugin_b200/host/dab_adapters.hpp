@@ -123,11 +123,11 @@ class Context {
     std::mutex m_mutex;
     std::string m_last_error;
 public:
-    Context(int transmission_mode, int iq_format = DABGPU_IQ_C32, unsigned flags = 0, int device = 0) {
+    Context(int transmission_mode, int iq_format = DABGPU_IQ_C32, unsigned flags = 0, int device = 0, int max_streams = 1) {
         dabgpu_config cfg;
         dabgpu_config_default(&cfg, transmission_mode);
         cfg.device = device;
-        cfg.max_streams = 1;
+        cfg.max_streams = max_streams;
         cfg.iq_format = iq_format;
         cfg.flags = flags;
         if (dabgpu_ctx_create(&cfg, &m_ctx) != DABGPU_OK) throw std::runtime_error(std::string("dabgpu_ctx_create: ") + dabgpu_last_error());
@@ -182,6 +182,9 @@ private:
     mutable dabgpu_ofdm_status m_status{};
     std::vector<viterbi_bit_t> m_frame_bits;
     dabgpu_frame_info m_frame_info{};
+    // GUI taps: fetched from the device when the getter is called (the render thread polls them, src/render_radio_block.cpp:96-214)
+    mutable std::vector<float> m_impulse_response, m_coarse_response;
+    mutable std::vector<std::complex<float>> m_frame_fft, m_frame_data_vec, m_correlation_time_buffer;
     Observable<span<const viterbi_bit_t>> m_obs_on_ofdm_frame;
     std::function<void()> m_on_device_frame;   // Radio_Block: channel-decode the frame where it is, on the device
     static bool same(const OFDM_Demod_Config& a, const OFDM_Demod_Config& b) { return memcmp(&a, &b, sizeof(a)) == 0; }
@@ -208,10 +211,16 @@ public:
     // tests pin them against the reference's.  nb_desired_threads has no meaning on the GPU.
     OFDM_Demod(const OFDM_Params& params, span<const std::complex<float>> prs_fft_ref, span<const int> carrier_mapper, int nb_desired_threads = 0,
                std::shared_ptr<Context> ctx = nullptr)
-        : m_params(params), m_ctx(ctx ? ctx : std::make_shared<Context>(mode_from_fft(params.nb_fft), DABGPU_IQ_C32)) {
+        : m_params(params), m_ctx(ctx ? ctx : std::make_shared<Context>(mode_from_fft(params.nb_fft), DABGPU_IQ_C32, DABGPU_FLAG_DIAG_TAPS)) {
         (void)prs_fft_ref; (void)carrier_mapper; (void)nb_desired_threads;
         m_p = query_params(mode_from_fft(params.nb_fft));
         m_frame_bits.resize(size_t(m_p.nb_frame_bits));
+        // same extents as the reference's buffers (ofdm_demodulator.cpp:97-110), zero until the first frame
+        m_impulse_response.assign(size_t(m_p.nb_fft), 0.0f);
+        m_coarse_response.assign(size_t(m_p.nb_fft), 0.0f);
+        m_frame_fft.assign(size_t(m_p.nb_frame_symbols + 1) * size_t(m_p.nb_fft), std::complex<float>(0.0f, 0.0f));
+        m_frame_data_vec.assign(size_t(m_p.nb_frame_symbols - 1) * size_t(m_p.nb_fft), std::complex<float>(0.0f, 0.0f));
+        m_correlation_time_buffer.assign(size_t(m_p.nb_null_period + m_p.nb_symbol_period), std::complex<float>(0.0f, 0.0f));
         memset(&m_cfg_applied, 0, sizeof(m_cfg_applied));
         m_cfg_applied = m_cfg;
     }
@@ -254,6 +263,34 @@ public:
     int GetTotalFramesRead() const { refresh_status(); return m_status.total_frames_read; }
     int GetTotalFramesDesync() const { refresh_status(); return m_status.total_frames_desync; }
     span<const viterbi_bit_t> GetFrameDataBits() const { return span<const viterbi_bit_t>(m_frame_bits.data(), m_frame_bits.size()); }
+    // The views below are refreshed from the device by the call and stay valid until the next call of the same getter.  They keep
+    // their previous content when the context has no taps (a caller-supplied Context without DABGPU_FLAG_DIAG_TAPS) or no frame
+    // was emitted yet.
+    span<const std::complex<float>> GetFrameFFT() const {   // (nb_frame_symbols + 1) x nb_fft, NULL symbol last
+        std::lock_guard<std::mutex> lock(m_ctx->mutex());
+        dabgpu_ofdm_get_frame_fft(m_ctx->get(), 0, reinterpret_cast<float*>(m_frame_fft.data()), m_frame_fft.size() * 2);
+        return span<const std::complex<float>>(m_frame_fft.data(), m_frame_fft.size());
+    }
+    span<const std::complex<float>> GetFrameDataVec() const {   // the reference's extent (L-1) x nb_fft, (L-1) x nb_data_carriers used
+        std::lock_guard<std::mutex> lock(m_ctx->mutex());
+        dabgpu_ofdm_get_frame_data_vec(m_ctx->get(), 0, reinterpret_cast<float*>(m_frame_data_vec.data()), m_frame_data_vec.size() * 2);
+        return span<const std::complex<float>>(m_frame_data_vec.data(), m_frame_data_vec.size());
+    }
+    span<const float> GetImpulseResponse() const {
+        std::lock_guard<std::mutex> lock(m_ctx->mutex());
+        dabgpu_ofdm_get_response(m_ctx->get(), 0, 0, m_impulse_response.data(), int(m_impulse_response.size()));
+        return span<const float>(m_impulse_response.data(), m_impulse_response.size());
+    }
+    span<const float> GetCoarseFrequencyResponse() const {
+        std::lock_guard<std::mutex> lock(m_ctx->mutex());
+        dabgpu_ofdm_get_response(m_ctx->get(), 0, 1, m_coarse_response.data(), int(m_coarse_response.size()));
+        return span<const float>(m_coarse_response.data(), m_coarse_response.size());
+    }
+    span<const std::complex<float>> GetCorrelationTimeBuffer() const {
+        std::lock_guard<std::mutex> lock(m_ctx->mutex());
+        dabgpu_ofdm_get_correlation_buffer(m_ctx->get(), 0, reinterpret_cast<float*>(m_correlation_time_buffer.data()), m_correlation_time_buffer.size() * 2);
+        return span<const std::complex<float>>(m_correlation_time_buffer.data(), m_correlation_time_buffer.size());
+    }
     auto& On_OFDM_Frame() { return m_obs_on_ofdm_frame; }
     // not in the reference: offsets in force when the frame being delivered to the observers was demodulated
     const dabgpu_frame_info& GetFrameInfo() const { return m_frame_info; }
@@ -409,36 +446,73 @@ inline dabgpu_subchannel to_abi(const Subchannel& s, bool is_dabplus) {
     return d;
 }
 
+// The stand-alone MSC_Decoder objects of a process share GPU contexts: a pool context has the single-CIF-per-frame geometry
+// (transmission mode II, FIC disabled) that gives DecodeCIF its one-CIF-at-a-time contract, and MSC_POOL_STREAMS streams; every
+// MSC_Decoder leases one stream of it (its own frame ring = its own CIF_Deinterleaver history).  A full pool is followed by
+// another one.  The reference builds one MSC_Decoder per sub-channel of a radio (basic_audio_channel.cpp), i.e. tens per process.
+constexpr int MSC_POOL_STREAMS = 32;
+class MscPool {
+    std::shared_ptr<Context> m_ctx;
+    std::vector<bool> m_used;
+public:
+    MscPool() : m_ctx(std::make_shared<Context>(2, DABGPU_IQ_U8, DABGPU_FLAG_NO_FIC, 0, MSC_POOL_STREAMS)), m_used(size_t(MSC_POOL_STREAMS), false) {}
+    const std::shared_ptr<Context>& context() const { return m_ctx; }
+    struct Lease { std::shared_ptr<MscPool> pool; int stream = -1; };
+    static Lease acquire() {
+        static std::mutex m;
+        static std::vector<std::weak_ptr<MscPool>> pools;
+        std::lock_guard<std::mutex> lock(m);
+        for (auto& w : pools)
+            if (auto p = w.lock())
+                for (int i = 0; i < MSC_POOL_STREAMS; i++)
+                    if (!p->m_used[size_t(i)]) { p->m_used[size_t(i)] = true; return Lease{p, i}; }
+        auto p = std::make_shared<MscPool>();
+        pools.push_back(p);
+        p->m_used[0] = true;
+        return Lease{p, 0};
+    }
+    void release(int stream) {
+        std::lock_guard<std::mutex> lock(m_ctx->mutex());
+        dabgpu_msc_configure(m_ctx->get(), stream, nullptr, 0);
+        m_used[size_t(stream)] = false;   // a later lease reconfigures the stream; its de-interleaver restarts empty
+    }
+};
+
 // One sub-channel of the common interleaved frame: CIF_Deinterleaver + EEP/UEP de-puncture + Viterbi + descramble.
-// The time de-interleaver history lives in the context's soft-bit ring; a private single-CIF-per-frame context
-// (transmission mode II geometry, FIC disabled) gives DecodeCIF its one-CIF-at-a-time contract.
+// The time de-interleaver history lives in the soft-bit frame ring of the leased stream.
 class MSC_Decoder {
     const Subchannel m_subchannel;
+    MscPool::Lease m_lease;
     std::shared_ptr<Context> m_ctx;
     std::vector<viterbi_bit_t> m_frame;
     std::vector<uint8_t> m_decoded_bytes_buf;
     dabgpu_params m_p;
     bool m_ok = false;
 public:
-    explicit MSC_Decoder(const Subchannel subchannel) : m_subchannel(subchannel), m_ctx(std::make_shared<Context>(2, DABGPU_IQ_U8, DABGPU_FLAG_NO_FIC)) {
+    explicit MSC_Decoder(const Subchannel subchannel) : m_subchannel(subchannel), m_lease(MscPool::acquire()), m_ctx(m_lease.pool->context()) {
         m_p = query_params(2);
         m_frame.assign(size_t(m_p.nb_frame_bits), 0);
         const dabgpu_subchannel d = to_abi(subchannel, false);
-        m_ok = m_ctx->check(dabgpu_msc_configure(m_ctx->get(), 0, &d, 1));
+        std::lock_guard<std::mutex> lock(m_ctx->mutex());
+        m_ok = m_ctx->check(dabgpu_msc_configure(m_ctx->get(), m_lease.stream, &d, 1));
         int nb = 0;
-        if (m_ok) dabgpu_msc_get_layout(m_ctx->get(), 0, 0, nullptr, &nb);
+        if (m_ok) dabgpu_msc_get_layout(m_ctx->get(), m_lease.stream, 0, nullptr, &nb);
         m_decoded_bytes_buf.resize(size_t(nb));
     }
+    ~MSC_Decoder() { m_lease.pool->release(m_lease.stream); }
+    MSC_Decoder(const MSC_Decoder&) = delete;
+    MSC_Decoder& operator=(const MSC_Decoder&) = delete;
     // Returns a view of the decoded bytes; empty while the 16-CIF de-interleaver is still filling (msc_decoder.cpp:46-75)
     span<uint8_t> DecodeCIF(span<const viterbi_bit_t> buf) {
         if (!m_ok || buf.size() != size_t(m_p.nb_cif_bits)) return span<uint8_t>();
         memcpy(m_frame.data() + m_p.nb_fic_bits, buf.data(), buf.size());
+        const int s = m_lease.stream;
         std::lock_guard<std::mutex> lock(m_ctx->mutex());
-        if (!m_ctx->check(dabgpu_softbits_push(m_ctx->get(), m_frame.data(), m_frame.size(), 0, 1))) return span<uint8_t>();
-        if (!m_ctx->check(dabgpu_chan_decode(m_ctx->get(), 0, 1))) return span<uint8_t>();
+        if (!m_ctx->check(dabgpu_softbits_push(m_ctx->get(), m_frame.data(), m_frame.size(), s, 1))) return span<uint8_t>();
+        if (!m_ctx->check(dabgpu_chan_decode(m_ctx->get(), s, 1))) return span<uint8_t>();
         uint8_t valid = 0;
         int nb = 0;
-        if (!m_ctx->check(dabgpu_chan_get_msc(m_ctx->get(), 0, 0, m_decoded_bytes_buf.data(), m_decoded_bytes_buf.size(), &valid, &nb))) return span<uint8_t>();
+        if (!m_ctx->check(dabgpu_chan_get_msc(m_ctx->get(), s, 0, m_decoded_bytes_buf.data(), m_decoded_bytes_buf.size(), &valid, &nb))) return span<uint8_t>();
         return valid ? span<uint8_t>(m_decoded_bytes_buf.data(), size_t(nb)) : span<uint8_t>();
     }
     bool IsValid() const { return m_ok; }
@@ -577,16 +651,21 @@ private:
     FIC_Autoconfig m_autocfg;
     bool m_self_configure = false;
     std::vector<uint8_t> m_configured_ids;
-    // BasicRadio::UpdateAfterProcessing (basic_radio.cpp:83-154): new complete audio sub-channels get a decoder and observers
-    // are told.  The GPU context is reconfigured as a whole, so every de-interleaver restarts when the set grows.
+    std::vector<uint8_t> m_rejected_ids;
+    // BasicRadio::UpdateAfterProcessing (basic_radio.cpp:83-154): every newly complete audio sub-channel gets a decoder
+    // (dabgpu_msc_add_subchannel) and the observers are told; the decoders already running keep their de-interleaver and
+    // superframe state.  A sub-channel the context refuses only affects itself and is not retried.
     void update_after_processing() {
         std::vector<dabgpu_subchannel> subs;
         std::vector<uint8_t> ids;
         m_autocfg.Runnable(subs, ids);
-        if (ids == m_configured_ids) return;
-        if (!m_ctx->check(dabgpu_msc_configure(m_ctx->get(), 0, subs.data(), int(subs.size())))) return;
-        std::vector<std::unique_ptr<Channel>> channels;
         for (size_t i = 0; i < subs.size(); i++) {
+            bool known = false;
+            for (uint8_t k : m_configured_ids) known = known || (k == ids[i]);
+            for (uint8_t k : m_rejected_ids) known = known || (k == ids[i]);
+            if (known) continue;
+            int index = -1;
+            if (!m_ctx->check(dabgpu_msc_add_subchannel(m_ctx->get(), 0, &subs[i], &index))) { m_rejected_ids.push_back(ids[i]); continue; }
             auto ch = std::make_unique<Channel>();
             ch->subchannel.id = ids[i];
             ch->subchannel.start_address = uint16_t(subs[i].start_address);
@@ -596,15 +675,10 @@ private:
             ch->subchannel.eep_prot_level = uint8_t(subs[i].eep_prot_level);
             ch->subchannel.eep_type = subs[i].eep_type_b ? EEP_Type::TYPE_B : EEP_Type::TYPE_A;
             ch->is_dabplus = subs[i].is_dabplus != 0;
-            channels.push_back(std::move(ch));
-        }
-        const std::vector<uint8_t> known = m_configured_ids;
-        m_channels = std::move(channels);
-        m_configured_ids = ids;
-        for (size_t i = 0; i < ids.size(); i++) {
-            bool is_new = true;
-            for (uint8_t k : known) is_new = is_new && (k != ids[i]);
-            if (is_new) m_obs_audio_channel.Notify(ids[i], *m_channels[i]);
+            if (size_t(index) != m_channels.size()) continue;   // cannot happen while this object is the only writer of the table
+            m_channels.push_back(std::move(ch));
+            m_configured_ids.push_back(ids[i]);
+            m_obs_audio_channel.Notify(ids[i], *m_channels.back());
         }
     }
     void deliver() {

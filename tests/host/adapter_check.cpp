@@ -210,8 +210,56 @@ static void run_selfcfg(Reader& in, Writer& out) {
     out.i32(int32_t(radio.GetTotalChannels()));
 }
 
+// n_decoders, per decoder a sub-channel, n_cifs, then per CIF index one CIF of 55296 soft bits per decoder.  Several MSC_Decoder
+// objects alive at once share a pool context (host/dab_adapters.hpp MscPool), one leased stream each; a decoder destroyed and
+// re-created in between must start with an empty de-interleaver.
+static void run_mscpool(Reader& in, Writer& out) {
+    const int n_dec = in.i32();
+    std::vector<Subchannel> subs;
+    for (int i = 0; i < n_dec; i++) subs.push_back(read_sub(in, nullptr));
+    const int n_cifs = in.i32();
+    { MSC_Decoder scratch(subs[0]); const std::vector<int8_t> z(55296, 0); scratch.DecodeCIF(span<const viterbi_bit_t>(z.data(), z.size())); }   // leases and returns stream 0
+    std::vector<std::unique_ptr<MSC_Decoder>> dec;
+    for (int i = 0; i < n_dec; i++) {
+        dec.push_back(std::make_unique<MSC_Decoder>(subs[size_t(i)]));
+        if (!dec.back()->IsValid()) { std::cerr << "MSC_Decoder: " << dec.back()->LastError() << "\n"; exit(2); }
+    }
+    for (int c = 0; c < n_cifs; c++)
+        for (int i = 0; i < n_dec; i++) {
+            const int8_t* cif = reinterpret_cast<const int8_t*>(in.bytes(55296));
+            auto bytes = dec[size_t(i)]->DecodeCIF(span<const viterbi_bit_t>(cif, 55296));
+            out.i32(int32_t(bytes.size()));
+            out.bytes(bytes.data(), bytes.size());
+        }
+}
+
+// mode, block, n_samples, u8 IQ through Create_OFDM_Demodulator; then the GUI getters of OFDM_Demod (ofdm_demodulator.h:135-139,
+// polled by src/render_radio_block.cpp:96-214): sizes and contents as floats.
+static void run_taps(Reader& in, Writer& out) {
+    const int mode = in.i32(), block = in.i32(), n_samples = in.i32();
+    const uint8_t* u8 = in.bytes(size_t(n_samples) * 2);
+    auto demod = Create_OFDM_Demodulator(mode, 1);
+    std::vector<std::complex<float>> blockbuf(static_cast<size_t>(block));
+    for (int off = 0; off + block <= n_samples; off += block) {
+        for (int i = 0; i < block; i++)
+            blockbuf[size_t(i)] = std::complex<float>((float(u8[2 * (off + i)]) - 127.5f) * (1.0f / 127.5f), (float(u8[2 * (off + i) + 1]) - 127.5f) * (1.0f / 127.5f));
+        demod->Process(span<const std::complex<float>>(blockbuf.data(), blockbuf.size()));
+    }
+    out.i32(demod->GetTotalFramesRead());
+    const auto imp = demod->GetImpulseResponse();
+    out.i32(int32_t(imp.size())); out.bytes(imp.data(), imp.size() * sizeof(float));
+    const auto coarse = demod->GetCoarseFrequencyResponse();
+    out.i32(int32_t(coarse.size())); out.bytes(coarse.data(), coarse.size() * sizeof(float));
+    const auto fft = demod->GetFrameFFT();
+    out.i32(int32_t(fft.size())); out.bytes(fft.data(), fft.size() * sizeof(std::complex<float>));
+    const auto vec = demod->GetFrameDataVec();
+    out.i32(int32_t(vec.size())); out.bytes(vec.data(), vec.size() * sizeof(std::complex<float>));
+    const auto corr = demod->GetCorrelationTimeBuffer();
+    out.i32(int32_t(corr.size())); out.bytes(corr.data(), corr.size() * sizeof(std::complex<float>));
+}
+
 int main(int argc, char** argv) {
-    if (argc != 4) { std::cerr << "usage: adapter_check <viterbi|fic|msc|rs|aac|radio|selfcfg> in.bin out.bin\n"; return 1; }
+    if (argc != 4) { std::cerr << "usage: adapter_check <viterbi|fic|msc|mscpool|rs|aac|radio|selfcfg|taps> in.bin out.bin\n"; return 1; }
     try {
         Reader in(argv[2]);
         Writer out;
@@ -223,6 +271,8 @@ int main(int argc, char** argv) {
         else if (what == "aac") run_aac(in, out);
         else if (what == "radio") run_radio(in, out);
         else if (what == "selfcfg") run_selfcfg(in, out);
+        else if (what == "mscpool") run_mscpool(in, out);
+        else if (what == "taps") run_taps(in, out);
         else { std::cerr << "unknown test " << what << "\n"; return 1; }
         out.save(argv[3]);
     } catch (const std::exception& e) {

@@ -303,3 +303,72 @@ def test_basic_radio_configures_itself_from_the_fic(driver, tx, pyref):
         got = data.get(s.id, [])
         assert len(got) == len(exp) > 0, s.id
         assert all(np.array_equal(g, e) for g, e in zip(got, exp)), s.id
+
+
+def test_msc_decoder_objects_share_a_pool_context(driver, tx, pyref):
+    """Three MSC_Decoder objects alive at once (one leased stream each of a shared pool context), fed interleaved: each equals its
+    own oracle decoder.  The first one re-uses a stream that another decoder held before: it must start empty."""
+    scs = [tx.Subchannel(0, 12, 48, eep_level=2), tx.Subchannel(1, 100, 35, is_uep=True, uep_index=4, dabplus=False),
+           tx.Subchannel(2, 300, 42, eep_level=1, eep_type_b=True, dabplus=False)]
+    rng = np.random.default_rng(18)
+    n_cifs = 20
+    cifs = [[rng.integers(-127, 128, size=55296).astype(np.int8) for _ in scs] for _ in range(n_cifs)]
+    payload = _i32(len(scs))
+    for sc in scs:
+        payload += _i32(sc.id, sc.start_address, sc.length, int(sc.is_uep), sc.uep_index, sc.eep_level, int(sc.eep_type_b), 0)
+    payload += _i32(n_cifs) + b"".join(c.tobytes() for row in cifs for c in row)
+    out = _run(driver, "mscpool", payload)
+    mk = pyref.RefMsc if pyref.ref_available() else pyref.PortMsc
+    o = [mk(sc.start_address, sc.length, sc.is_uep, sc.uep_index, sc.eep_level, sc.eep_type_b) for sc in scs]
+    off, n_valid = 0, 0
+    for row in cifs:
+        for k, c in enumerate(row):
+            n, = struct.unpack_from("<i", out, off)
+            got = np.frombuffer(out, dtype=np.uint8, count=n, offset=off + 4)
+            off += 4 + n
+            exp = o[k].decode_cif(c)
+            assert n == exp.size and np.array_equal(got, exp), k
+            n_valid += int(n > 0)
+    assert n_valid == len(scs) * (n_cifs - 15)
+
+
+def test_ofdm_demod_class_serves_the_gui_getters(driver, tx, pyref, ref_ok):
+    """OFDM_Demod::GetImpulseResponse / GetCoarseFrequencyResponse / GetFrameFFT / GetFrameDataVec / GetCorrelationTimeBuffer
+    (ofdm_demodulator.h:135-140, read by src/render_radio_block.cpp:96-214) through the C++ adapter: the reference's extents,
+    contents within the tolerances of tests/test_ofdm_gpu.py::test_gui_taps_match_reference."""
+    mode, block = 1, 65536
+    ens = tx.EnsembleTx(mode, tx.default_ensemble(), seed=5)
+    iq = tx.ofdm_modulate([ens.next_frame_bits() for _ in range(4)], mode)
+    u8 = tx.to_u8(tx.impair(iq, 18.0, 1.7e-3, 2222, seed=6, tail_samples=3000), 30.0)
+    n = (u8.size // 2 // block) * block
+    out = _run(driver, "taps", _i32(mode, block, n) + u8[:2 * n].tobytes())
+    ref = pyref.RefOfdm(mode, 1)
+    c32 = ((u8[:2 * n].astype(np.float32) - np.float32(127.5)) * np.float32(1.0 / 127.5)).view(np.complex64)
+    for off in range(0, n, block):
+        ref.process_c32(c32[off:off + block])
+    P = importlib.import_module(PKG).get_params(mode)
+    N, L, K = P.nb_fft, P.nb_frame_symbols, P.nb_data_carriers
+    off = 0
+    frames, = struct.unpack_from("<i", out, off); off += 4
+    assert frames == len(ref.pop_frames()) >= 2
+
+    def take(dtype, per):
+        nonlocal off
+        cnt, = struct.unpack_from("<i", out, off)
+        a = np.frombuffer(out, dtype=dtype, count=cnt, offset=off + 4)
+        off += 4 + cnt * per
+        return a
+
+    imp, coarse = take(np.float32, 4), take(np.float32, 4)
+    fft, vec, corr = take(np.complex64, 8), take(np.complex64, 8), take(np.complex64, 8)
+    assert imp.size == N and coarse.size == N and fft.size == (L + 1) * N and vec.size == (L - 1) * N and corr.size == P.nb_null_period + P.nb_symbol_period
+    for got, exp in ((imp, ref.impulse_response(N)), (coarse, ref.coarse_response(N))):
+        assert int(np.argmax(got)) == int(np.argmax(exp))
+        strong = exp > exp.max() - 40.0
+        assert np.abs(got[strong] - exp[strong]).max() < 0.05
+    exp_fft = ref.frame_fft((L + 1) * N)
+    scale = np.abs(exp_fft).max()
+    assert np.abs(fft - exp_fft).max() < 2e-3 * scale
+    exp_vec = ref.frame_data_vec((L - 1) * K)
+    assert np.abs(vec[:(L - 1) * K] - exp_vec).max() < 4e-3 * np.abs(exp_vec).max()
+    assert np.array_equal(corr, ref.correlation_buffer(corr.size))   # raw input samples: identical

@@ -233,11 +233,21 @@ def test_gui_taps_match_reference(gpu_ctx, tx, pyref, ref_ok, mode):
         strong = exp > exp.max() - 40.0
         assert strong.sum() > 0 and np.abs(got[strong] - exp[strong]).max() < 0.05, (kind, np.abs(got[strong] - exp[strong]).max())
     # OFDM_Demod::GetFrameFFT: PRS + data symbol spectra of the last emitted frame (the reference appends the NULL symbol row)
-    L = g.P.nb_frame_symbols
-    exp_fft = ref.frame_fft((L + 1) * n).reshape(L + 1, n)[:L]
+    L, K = g.P.nb_frame_symbols, g.P.nb_data_carriers
+    exp_all = ref.frame_fft((L + 1) * n).reshape(L + 1, n)
+    exp_fft = exp_all[:L]
     got_fft = g.ofdm_frame_fft(0)
     scale = np.abs(exp_fft).max()
     assert scale > 0 and np.abs(got_fft - exp_fft).max() < 2e-3 * scale, np.abs(got_fft - exp_fft).max() / scale
+    # with room for L + 1 rows the NULL-symbol row comes too (noise only here: same absolute tolerance as the data rows)
+    got_all = g.ofdm_frame_fft(0, with_null=True)
+    assert np.array_equal(got_all[:L], got_fft)
+    assert np.abs(exp_all[L]).max() > 0 and np.abs(got_all[L] - exp_all[L]).max() < 2e-3 * scale, np.abs(got_all[L] - exp_all[L]).max() / scale
+    # OFDM_Demod::GetFrameDataVec: X_i * conj(X_{i+1}) on the K data carriers, (L-1) rows packed with stride K
+    exp_vec = ref.frame_data_vec((L - 1) * K).reshape(L - 1, K)
+    got_vec = g.ofdm_frame_data_vec(0)
+    vscale = np.abs(exp_vec).max()
+    assert vscale > 0 and np.abs(got_vec - exp_vec).max() < 4e-3 * vscale, np.abs(got_vec - exp_vec).max() / vscale
     with pytest.raises(gpu_ctx.DabGpuError):
         plain.ofdm_response(0, 0)        # taps are opt-in: the context was created without the flag
     with pytest.raises(gpu_ctx.DabGpuError):
