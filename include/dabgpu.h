@@ -84,6 +84,11 @@ DABGPU_API void dabgpu_config_default(dabgpu_config* cfg, int transmission_mode)
 DABGPU_API int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out);
 DABGPU_API void dabgpu_ctx_destroy(dabgpu_ctx* ctx);
 DABGPU_API int dabgpu_sync(dabgpu_ctx* ctx);                       /* wait for all queued work */
+/* Page-locked host memory for the buffers handed to dabgpu_submit / dabgpu_ofdm_process (copies from pageable memory neither
+ * overlap nor reach the link rate).  write_combined != 0: for input buffers the CPU only ever writes.  Allocate on a thread
+ * that is bound to the NUMA node of the GPU: the pages are placed where the calling thread runs. */
+DABGPU_API int dabgpu_host_alloc(void** out, size_t bytes, int write_combined);
+DABGPU_API void dabgpu_host_free(void* p);
 DABGPU_API void* dabgpu_cuda_stream(dabgpu_ctx* ctx);              /* the stream every kernel is launched on */
 /* number of kernels of this library launched on the context so far (bench.py "gpu_launches") */
 DABGPU_API uint64_t dabgpu_launch_count(const dabgpu_ctx* ctx);

@@ -503,7 +503,8 @@ API double ref_time_ofdm_u8(int mode, const uint8_t* iq, long n_samples, int blo
 // Whole receive chain on the CPU, one stream, one thread of control: OFDM_Demod (serial driver, threads=1) -> 4 x
 // FIC_Decoder::DecodeFIBGroup + MSC_Decoder::DecodeCIF per sub-channel and CIF + AAC_Frame_Processor::Process for the
 // DAB+ sub-channels.  subs = n_subs x {start_address, length, is_uep, uep_index, eep_level, eep_type_b, is_dabplus}.
-// counts_out = {frames, fibs_ok, msc_bytes, access_units}.  Returns seconds of wall time.
+// counts_out[8] = {frames, fibs_ok, msc_bytes, access_units, superframe headers, RS errors, AU CRC errors, firecode errors} (observer
+// events of all sub-channels; bench.py's spot check compares them with the GPU's counters).  Returns seconds of wall time.
 API double ref_time_chain_u8(int mode, const uint8_t* iq, long n_samples, int block_size, int repeat, const int* subs, int n_subs,
                              long long* counts_out) {
     int dp[13];
@@ -521,7 +522,7 @@ API double ref_time_chain_u8(int mode, const uint8_t* iq, long n_samples, int bl
     }
     std::vector<int8_t> frame(static_cast<size_t>(P.nb_frame_bits));
     std::vector<uint8_t> bytes(8192), log(1 << 16), fibs(30*8);
-    long long frames = 0, fibs_ok = 0, msc_bytes = 0, aus = 0;
+    long long frames = 0, fibs_ok = 0, msc_bytes = 0, aus = 0, headers = 0, rs_err = 0, au_crc = 0, fire = 0;
     const auto t0 = std::chrono::steady_clock::now();
     for (int rep = 0; rep < repeat; rep++) {
         for (long off = 0; off < n_samples; off += block_size) {
@@ -547,6 +548,10 @@ API double ref_time_chain_u8(int mode, const uint8_t* iq, long n_samples, int bl
                                     int32_t hdr[6];
                                     memcpy(hdr, &a->log[o], 24);
                                     if (hdr[0] == EV_AU) aus++;
+                                    else if (hdr[0] == EV_HEADER) headers++;
+                                    else if (hdr[0] == EV_RS_ERROR) rs_err++;
+                                    else if (hdr[0] == EV_AU_CRC_ERROR) au_crc++;
+                                    else if (hdr[0] == EV_FIRECODE_ERROR) fire++;
                                     o += 24 + ((size_t(hdr[5]) + 3u) & ~size_t(3));
                                 }
                             }
@@ -557,7 +562,10 @@ API double ref_time_chain_u8(int mode, const uint8_t* iq, long n_samples, int bl
         }
     }
     const auto t1 = std::chrono::steady_clock::now();
-    if (counts_out) { counts_out[0] = frames; counts_out[1] = fibs_ok; counts_out[2] = msc_bytes; counts_out[3] = aus; }
+    if (counts_out) {
+        counts_out[0] = frames; counts_out[1] = fibs_ok; counts_out[2] = msc_bytes; counts_out[3] = aus;
+        counts_out[4] = headers; counts_out[5] = rs_err; counts_out[6] = au_crc; counts_out[7] = fire;
+    }
     for (auto* m : msc) ref_msc_destroy(m);
     for (auto* a : aac) if (a) ref_aac_destroy(a);
     ref_fic_destroy(fic);

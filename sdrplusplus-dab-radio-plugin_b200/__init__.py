@@ -102,7 +102,7 @@ EXPORTS = [
     "dabgpu_get_counters", "dabgpu_submit", "dabgpu_wait", "dabgpu_msc_get_layout",
     "dabgpu_ofdm_set_config", "dabgpu_fic_decode", "dabgpu_dabplus_open", "dabgpu_dabplus_close", "dabgpu_dabplus_process",
     "dabgpu_autocfg_create", "dabgpu_autocfg_destroy", "dabgpu_autocfg_push_fibs", "dabgpu_autocfg_dump", "dabgpu_autocfg_runnable",
-    "dabgpu_ofdm_get_frame_data_vec", "dabgpu_ofdm_get_correlation_buffer", "dabgpu_autocfg_applied", "dabgpu_msc_add_subchannel", "dabgpu_msc_remove_subchannel", "dabgpu_chan_join",
+    "dabgpu_host_alloc", "dabgpu_host_free", "dabgpu_ofdm_get_frame_data_vec", "dabgpu_ofdm_get_correlation_buffer", "dabgpu_autocfg_applied", "dabgpu_msc_add_subchannel", "dabgpu_msc_remove_subchannel", "dabgpu_chan_join",
     "dabgpu_autocfg_apply", "dabgpu_ofdm_get_response", "dabgpu_ofdm_get_frame_fft", "dabgpu_iq_convert", "dabgpu_softbits_to_bytes", "dabgpu_bytes_to_softbits",
 ]
 
@@ -125,6 +125,9 @@ def load_library() -> C.CDLL:
     L.dabgpu_ctx_destroy.argtypes = [C.c_void_p]
     L.dabgpu_ctx_destroy.restype = None
     L.dabgpu_sync.argtypes = [C.c_void_p]
+    L.dabgpu_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]
+    L.dabgpu_host_free.argtypes = [C.c_void_p]
+    L.dabgpu_host_free.restype = None
     L.dabgpu_cuda_stream.argtypes = [C.c_void_p]
     L.dabgpu_cuda_stream.restype = C.c_void_p
     L.dabgpu_launch_count.argtypes = [C.c_void_p]
@@ -183,6 +186,29 @@ def load_library() -> C.CDLL:
 def _check(rc: int):
     if rc != OK:
         raise DabGpuError(rc, load_library().dabgpu_last_error().decode(errors="replace"))
+
+
+class HostBuffer:
+    """Page-locked host memory from dabgpu_host_alloc, viewed as a numpy uint8 array (`.array`)."""
+
+    def __init__(self, nbytes: int, write_combined: bool = False):
+        self.L = load_library()
+        self.ptr = C.c_void_p()
+        _check(self.L.dabgpu_host_alloc(C.byref(self.ptr), nbytes, int(write_combined)))
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr.value))
+
+    def close(self):
+        if getattr(self, "ptr", None) and self.ptr.value:
+            self.array = None
+            self.L.dabgpu_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def get_params(mode: int) -> Params:

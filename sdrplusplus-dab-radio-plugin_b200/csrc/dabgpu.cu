@@ -329,6 +329,17 @@ void dabgpu_ctx_destroy(dabgpu_ctx* ctx) {
     delete ctx;
 }
 
+// Pinned host memory for dabgpu_submit / dabgpu_ofdm_process buffers.  write_combined: for buffers the CPU only writes (the IQ
+// the host feeds in): uncached on the CPU side, so the copy engine's reads do not snoop the CPU caches.
+int dabgpu_host_alloc(void** out, size_t bytes, int write_combined) {
+    if (!out) return set_error(DABGPU_ERR_INVALID, "null output");
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_error(DABGPU_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+    return DABGPU_OK;
+}
+void dabgpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int dabgpu_sync(dabgpu_ctx* ctx) {
     if (!ctx) return set_error(DABGPU_ERR_INVALID, "null context");
     CUDA_TRY(sync_ctx(ctx));

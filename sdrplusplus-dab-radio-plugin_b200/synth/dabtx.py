@@ -592,3 +592,25 @@ def hard_to_soft(bits: np.ndarray, rng: Optional[np.random.Generator] = None, sn
 def default_ensemble() -> List[Subchannel]:
     """Config 1 of SURVEY.md 8(d): 18 DAB+ sub-channels EEP 3-A 48 CU filling 864 CU."""
     return [Subchannel(id=i, start_address=48 * i, length=48, eep_level=2, eep_type_b=False) for i in range(18)]
+
+
+def periodic_frames(mode: int, subchannels: Sequence[Subchannel], seed: int, period_frames: int) -> np.ndarray:
+    """[period_frames, nb_frame_bits] coded transmission frames whose endless repetition is a valid transmission: the logical
+    frames of every sub-channel repeat with the period (a whole number of 5-CIF DAB+ superframes), hence so do the
+    time-interleaved CIFs once the 16-CIF interleaver has filled.  Used to feed throughput runs of any length from a short buffer."""
+    p = MODES[mode]
+    period_cifs = period_frames * p.nb_cifs
+    assert period_cifs % 5 == 0 and period_cifs >= 16, "the period must hold whole superframes and at least the interleaver depth"
+    ens = EnsembleTx(mode, subchannels, seed=seed, fill_random=False)
+    cache = {sc.id: [] for sc in ens.subchannels}
+    fresh = ens._next_logical_frame
+
+    def replay(sc: Subchannel) -> np.ndarray:
+        if ens.cif_count < period_cifs:
+            cache[sc.id].append(fresh(sc))
+            return cache[sc.id][-1]
+        return cache[sc.id][ens.cif_count % period_cifs]
+
+    ens._next_logical_frame = replay
+    frames = [ens.next_frame_bits() for _ in range(2 * period_frames)]
+    return np.stack(frames[period_frames:])

@@ -69,3 +69,54 @@ def make_streams_u8(n_streams: int, n_frames: int, mode: int = 1, seed0: int = 1
         v = torch.clamp(torch.trunc(v * rms_lsb + 127.5), 0, 255).to(torch.uint8)
         out[s] = v.reshape(-1)
     return out
+
+
+def make_cyclic_streams_u8(n_streams: int, payload_bits: np.ndarray, mode: int = 1, seed0: int = 1, snr_db: float = 15.0,
+                           cfo_norm_max: float = 20e3 / 2.048e6, device: str = "cuda", rms_lsb: float = 30.0):
+    """One PERIOD of every stream: uint8 [n_streams, 2*P*frame_samples] that can be repeated back to back for ever.
+    payload_bits: [n_unique, P, frame_bits] coded frames whose content is periodic with period P (bench.py: periodic_payload).
+    Stream s is the P-frame signal of payload s % n_unique rotated by its timing lead (uniform in [0, frame_samples)), with a
+    CFO uniform in +-cfo_norm_max rounded to a whole number of cycles per period (no phase jump where the period repeats) and
+    one period of AWGN.  Returns (tensor, cfos, leads)."""
+    p = dabtx.MODES[mode]
+    K, N, CP, T = p.nb_carriers, p.nb_fft, p.nb_cyclic_prefix, p.nb_symbol_period
+    L = p.nb_frame_symbols
+    fs = p.nb_frame_samples
+    P = int(payload_bits.shape[1])
+    total = P * fs
+    dev = torch.device(device)
+    cmap = torch.from_numpy(dabtx.carrier_map(N, K)).to(dev)
+    slot_k = np.concatenate([np.arange(-K // 2, 0), np.arange(1, K // 2 + 1)])
+    slot_bin = torch.from_numpy((slot_k % N).astype(np.int64)).to(dev)
+    prs = torch.from_numpy(np.exp(1j * np.pi / 2 * dabtx.prs_phase_index(mode)).astype(np.complex64)).to(dev)
+    out = torch.empty((n_streams, 2 * total), dtype=torch.uint8, device=dev)
+    pb = torch.from_numpy(np.ascontiguousarray(payload_bits)).to(dev)
+    rng = np.random.default_rng(seed0)
+    cfos = np.round(rng.uniform(-cfo_norm_max, cfo_norm_max, size=n_streams) * total) / total
+    leads = rng.integers(0, fs, size=n_streams)
+    sigma = math.sqrt(0.5 * 10 ** (-snr_db / 10))
+    n_idx = torch.arange(total, device=dev, dtype=torch.float64)
+    clean = []
+    for u in range(pb.shape[0]):      # the modulated period of every unique ensemble, once
+        bits = pb[u].reshape(P, L - 1, 2 * K)
+        q_pair = torch.complex(1 - 2 * bits[:, :, :K].to(torch.float32), 1 - 2 * bits[:, :, K:].to(torch.float32)) * (1 / math.sqrt(2.0))
+        q = torch.empty_like(q_pair)
+        q[:, :, cmap] = q_pair
+        cur = prs[None, None, :] * torch.cumprod(q, dim=1)
+        cur = cur / cur.abs()
+        slots = torch.cat([prs[None, None, :].expand(P, 1, K), cur], dim=1)
+        spec = torch.zeros((P, L, N), dtype=torch.complex64, device=dev)
+        spec[:, :, slot_bin] = slots
+        t = torch.fft.ifft(spec, dim=-1) * (N / math.sqrt(K))
+        syms = torch.cat([t[..., N - CP:], t], dim=-1).reshape(P, L * T)
+        clean.append(torch.cat([torch.zeros((P, p.nb_null_period), dtype=torch.complex64, device=dev), syms], dim=1).reshape(-1))
+    for s in range(n_streams):
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed0 * 100003 + s)
+        x = torch.roll(clean[s % len(clean)], int(leads[s]))
+        ph = torch.remainder(n_idx * float(cfos[s]), 1.0).to(torch.float32) * (2 * math.pi)
+        x = x * torch.complex(torch.cos(ph), torch.sin(ph))
+        noise = torch.randn((total, 2), generator=g, device=dev, dtype=torch.float32) * sigma
+        v = torch.view_as_real(x) + noise
+        out[s] = torch.clamp(torch.trunc(v * rms_lsb + 127.5), 0, 255).to(torch.uint8).reshape(-1)
+    return out, cfos, leads

@@ -288,7 +288,7 @@ def test_channel_stream_overlap_is_invisible(gpu_ctx, tx, pyref, monkeypatch):
                 assert all(np.array_equal(o, exp) for o in outs) and all(int(e) == exp_err for e in perr)
                 extra = outs[0]
             if f == 5:
-                g.msc_configure(0, subs)   # reconfiguration while a decode may be in flight: de-interleavers restart
+                g.msc_configure(0, subs)   # re-declaring the table while a decode may be in flight (unchanged entries keep their state)
             fibs, ok = g.get_fic(0)
             item = [fibs.copy(), ok.copy()]
             for k, sc in enumerate(subs):
