@@ -383,6 +383,22 @@ int dabo_msc_decode_cif(dabo_msc* m, const int8_t* cif, int n_bits, uint8_t* out
     if (m->is_uep) nseg = dabo_uep_segments(m->uep_index, pi, nb);
     else           nseg = dabo_eep_segments(m->length, m->eep_level, m->eep_type_b, pi, nb);
     if (nseg < 0) return 0;
+    /* A segment whose punctured symbols no longer fit the sub-channel decodes nothing and consumes nothing: depuncture_symbols
+     * returns an all-zero result when a block runs out of input (dab_viterbi_decoder.cpp:157-161) and DecodeUEP / DecodeEEP go on
+     * with the next update() (msc_decoder.cpp:86-96, 128-139).  Hits UEP row 34, which the reference's table lists with 64 CU. */
+    {
+        int remaining = m->nb_bits, k = 0;
+        for (int i = 0; i < nseg; i++) {
+            int need = 0;
+            uint8_t cnt[8] = {2, 2, 2, 2, 2, 2, 2, 2};            /* PI_X keeps 2 of every 4 mother bits */
+            if (pi[i] != 0) dabo_pi_counts(pi[i], cnt);
+            for (int g = 0; g < nb[i]/4; g++) need += cnt[g % 8];
+            if (need > remaining) continue;
+            remaining -= need;
+            pi[k] = pi[i]; nb[k] = nb[i]; k++;
+        }
+        nseg = k;
+    }
     int steps = 0;
     for (int i = 0; i < nseg; i++) steps += nb[i]/4;
     const int n_bytes = (steps - 6)/8;

@@ -57,6 +57,7 @@
 #include "dab/audio/aac_frame_processor.h"
 #include "dab/constants/dab_parameters.h"
 #include "dab/constants/puncture_codes.h"
+#include "dab/constants/subchannel_protection_tables.h"
 #include "dab/database/dab_database_entities.h"
 #include "dab/fic/fic_decoder.h"
 #include "dab/msc/cif_deinterleaver.h"
@@ -156,6 +157,16 @@ API int ref_fic_decode_group(void* h, const int8_t* bits, int n_bits, int cif_in
 // MSC sub-channel decoder
 // ---------------------------------------------------------------------------------------------
 struct RefMsc { std::unique_ptr<MSC_Decoder> dec; };
+
+// UEP_PROTECTION_TABLE row (dab/constants/subchannel_protection_tables.h:21-86): {size CU, bitrate, level, L1..L4, PI1..PI4, padding bits}
+API int ref_uep_descriptor(int index, int* out12) {
+    if (index < 0 || index >= UEP_PROTECTION_TABLE_SIZE) return -1;
+    const UEP_Descriptor& d = UEP_PROTECTION_TABLE[index];
+    out12[0] = d.subchannel_size; out12[1] = d.bitrate; out12[2] = d.protection_level;
+    for (int i = 0; i < 4; i++) { out12[3 + i] = d.Lx[i]; out12[7 + i] = d.PIx[i]; }
+    out12[11] = d.total_padding_bits;
+    return 0;
+}
 
 API void* ref_msc_create(int start_address, int length, int is_uep, int uep_index, int eep_level, int eep_type_b) {
     Subchannel sc(0);

@@ -216,6 +216,27 @@ static int make_schedule(const dabgpu_subchannel& sc, Schedule* out) {
     s.pi[s.n_seg] = 0;
     s.bits[s.n_seg] = 24;
     s.n_seg++;
+    // A segment whose punctured symbols do not fit what is left of the sub-channel decodes NOTHING and consumes nothing in the
+    // reference: depuncture_symbols returns an all-zero result as soon as a 4-bit block runs out of input
+    // (dab_viterbi_decoder.cpp:157-161) and DecodeUEP / DecodeEEP carry on with the next update() from the same position
+    // (msc_decoder.cpp:86-96, 128-139).  UEP_PROTECTION_TABLE row 34 is listed with 64 CU but needs 84 (rows 33 and 34 are
+    // swapped against EN 300 401 table 8): its third segment is skipped and 140 bytes per CIF come out.  Same rule here.
+    {
+        Schedule f;
+        int remaining = sc.length * 64;
+        for (int i = 0; i < s.n_seg; i++) {
+            int c[8], need = 0;
+            host_pi_counts(s.pi[i], c);
+            for (int g = 0; g < s.bits[i] / 4; g++) need += c[g % 8];
+            if (need > remaining) continue;
+            remaining -= need;
+            f.pi[f.n_seg] = s.pi[i];
+            f.bits[f.n_seg] = s.bits[i];
+            f.n_seg++;
+        }
+        s = f;
+    }
+    if (s.total_steps() < 6 + 8) return set_error(DABGPU_ERR_INVALID, "sub-channel of %d CU is too small for its protection profile", sc.length);
     *out = s;
     return DABGPU_OK;
 }
