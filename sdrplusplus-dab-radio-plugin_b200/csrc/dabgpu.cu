@@ -42,11 +42,12 @@ struct dabgpu_ctx {
     uint32_t vl_scratch_slots = 0;    // decoder warps the decision scratch is sized for
     int vl_ctas_forced = 0;           // test hook: 1 or 4 CTAs per SM regardless of the call size
     uint32_t vl_scratch_rows = 0;
-    struct { int first = -1, n = -1; uint64_t epoch = 0; uint32_t count[VL_BUCKETS]; uint32_t max_steps = 0; } vl_cache;
+    struct { int first = -1, n = -1; uint64_t epoch = 0; uint32_t count[VL_BUCKETS]; uint32_t max_steps = 0; uint32_t max_subs_used = 0; } vl_cache;
     uint64_t cfg_epoch = 1;
 
     // soft-bit frame ring + channel decode state
     DevBuf d_frames, d_frames_written, d_frames_decoded, d_frame_info;
+    DevBuf d_pushstage, d_popstage;   // natural-order frames on their way into / out of the ring (dabgpu_softbits_push, dabgpu_ofdm_pop_frames)
     DevBuf d_frames_snapshot;   // frames_written as the channel decode sees it (copied on the main stream before the fork)
     DevBuf d_subcfg, d_nsubs, d_cifs_consumed;
     DevBuf d_fic_out, d_fic_crc, d_msc_out, d_msc_valid, d_status, d_counters;
@@ -201,6 +202,10 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
         cudaError_t e = cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, int(VIT_SMEM_BYTES));
         if (e != cudaSuccess) { rc = set_error(DABGPU_ERR_CUDA, "cudaFuncSetAttribute(k_viterbi): %s", cudaGetErrorString(e)); dabgpu_ctx_destroy(ctx); return rc; }
     }
+    {
+        cudaError_t e = cudaFuncSetAttribute(k_vit_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, int(VP_SMEM_BYTES));
+        if (e != cudaSuccess) { rc = set_error(DABGPU_ERR_CUDA, "cudaFuncSetAttribute(k_vit_prep): %s", cudaGetErrorString(e)); dabgpu_ctx_destroy(ctx); return rc; }
+    }
     TRY_OR_FREE(ensure_scratch(ctx, 1600));
     TRY_OR_FREE(ctx->d_vlplan.alloc(sizeof(VlPlan)));
     ctx->vl_mode = (cfg->flags & DABGPU_FLAG_VIT_LANES_ALWAYS) ? 1 : ((cfg->flags & DABGPU_FLAG_VIT_LANES_NEVER) ? 2 : 0);
@@ -212,7 +217,7 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
 
     // frame ring + channel decode buffers
     const size_t frame_bits = size_t(P.nb_frame_bits);
-    TRY_OR_FREE(ctx->d_frames.alloc(size_t(S) * ctx->frame_slots * frame_bits));
+    TRY_OR_FREE(ctx->d_frames.alloc(size_t(S) * ctx->frame_slots * frame_bits + 1024));   // + slack: k_vit_prep reads whole 16-byte pieces of a plane / 256-byte units of a FIC group
     TRY_OR_FREE(ctx->d_frames_written.alloc(size_t(S) * 4));
     TRY_OR_FREE(ctx->d_frames_decoded.alloc(size_t(S) * 4));
     TRY_OR_FREE(ctx->d_frames_snapshot.alloc(size_t(S) * 4));
@@ -319,7 +324,7 @@ void dabgpu_ctx_destroy(dabgpu_ctx* ctx) {
     ofdm_destroy(ctx->ofdm);
     dabplus_destroy(ctx->dabplus);
     DevBuf* bufs[] = {&ctx->d_vlplan, &ctx->d_vllist, &ctx->d_vlsym, &ctx->d_vlscratch, &ctx->d_prbs, &ctx->d_counter, &ctx->d_scratch, &ctx->d_jobs, &ctx->d_vsoft, &ctx->d_vout, &ctx->d_verr,
-                      &ctx->d_frames, &ctx->d_frames_written, &ctx->d_frames_decoded, &ctx->d_frames_snapshot, &ctx->d_frame_info, &ctx->d_subcfg, &ctx->d_nsubs,
+                      &ctx->d_frames, &ctx->d_frames_written, &ctx->d_frames_decoded, &ctx->d_frames_snapshot, &ctx->d_pushstage, &ctx->d_popstage, &ctx->d_frame_info, &ctx->d_subcfg, &ctx->d_nsubs,
                       &ctx->d_cifs_consumed, &ctx->d_fic_out, &ctx->d_fic_crc, &ctx->d_msc_out, &ctx->d_msc_valid, &ctx->d_status,
                       &ctx->d_counters};
     for (DevBuf* b : bufs) b->release();
@@ -429,7 +434,8 @@ static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, 
         }
         k_vit_plan<<<1, 32, 0, ctx->stream>>>(plan, ctx->vl_mode, ctx->vl_min_jobs, rows, groups);
         k_vit_scatter<<<nb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, plan, ctx->d_vllist.as<uint32_t>());
-        k_vit_prep<<<groups, VP_WARPS * 32, 0, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(), ctx->d_vlsym.as<uint32_t>(), ctx->chan.geom);
+        k_vit_prep<<<(groups + VP_WARPS - 1u) / VP_WARPS, VP_WARPS * 32, VP_SMEM_BYTES, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(), ctx->d_vlsym.as<uint32_t>(),
+                                                                                               ctx->chan.geom);
         ctx->prof.end(ctx->stream);
         ctx->prof.begin(PROF_VITERBI, ctx->stream);
         if (!lanes_wide) {
@@ -461,7 +467,7 @@ int dabgpu_viterbi_decode(dabgpu_ctx* ctx, const dabgpu_viterbi_job* jobs, int n
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     CUDA_TRY(join_dabplus(ctx));   // shares the job, plan and scratch buffers with a channel decode that may still be running
     int rc;
-    if ((rc = ctx->d_vsoft.alloc(soft_bytes + 16))) return rc;
+    if ((rc = ctx->d_vsoft.alloc(soft_bytes + 1024))) return rc;   // k_vit_prep reads whole 256-byte units
     if ((rc = ctx->d_vout.alloc(out_bytes + 16))) return rc;
     if ((rc = ctx->d_verr.alloc(size_t(n_jobs) * 8))) return rc;
     if ((rc = ctx->d_jobs.alloc(size_t(n_jobs) * sizeof(VitJobDev)))) return rc;
@@ -685,12 +691,14 @@ int dabgpu_softbits_push(dabgpu_ctx* ctx, const int8_t* frames_host, size_t stri
         if (written[i] - decoded[i] >= ctx->chan.max_lag)
             return set_error(DABGPU_ERR_OVERFLOW, "soft-bit frame ring of stream %d is full (%u frames not channel-decoded yet): call dabgpu_chan_decode", first + i,
                              written[i] - decoded[i]);
-    for (int i = 0; i < n; i++) {
-        const size_t slot = written[i] & uint32_t(ctx->frame_slots - 1);
-        int8_t* dst = ctx->d_frames.as<int8_t>() + (size_t(first + i) * ctx->frame_slots + slot) * fb;
-        CUDA_TRY(cudaMemcpyAsync(dst, frames_host + size_t(i) * stride, fb, cudaMemcpyHostToDevice, ctx->stream));
-        written[i] += 1;
-    }
+    // natural-order frames -> staging -> ring layout (planar MSC); every stream writes the slot its counter points at
+    if ((rc = ctx->d_pushstage.alloc(size_t(n) * fb))) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(ctx->d_pushstage.p, fb, frames_host, stride, fb, size_t(n), cudaMemcpyHostToDevice, ctx->stream));
+    k_frame_convert<<<dim3(16, n), 256, 0, ctx->stream>>>(ctx->d_pushstage.as<int8_t>(), fb, ctx->d_frames.as<int8_t>() + size_t(first) * ctx->frame_slots * fb,
+                                                       size_t(ctx->frame_slots) * fb, ctx->d_frames_written.as<uint32_t>(), first, 0u, 0u, ctx->chan.geom, 1);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    for (int i = 0; i < n; i++) written[i] += 1;
     CUDA_TRY(cudaMemcpyAsync(ctx->d_frames_written.as<uint32_t>() + first, written, size_t(n) * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(sync_ctx(ctx));
     return DABGPU_OK;
@@ -825,7 +833,9 @@ static int chan_decode_body(dabgpu_ctx* ctx, int first, int n) {
     ctx->launches++;
     if (ctx->vl_cache.first != first || ctx->vl_cache.n != n || ctx->vl_cache.epoch != ctx->cfg_epoch) {
         VlBound vb;
+        ctx->vl_cache.max_subs_used = 0;
         for (int s = first; s < first + n; s++) {
+            ctx->vl_cache.max_subs_used = std::max(ctx->vl_cache.max_subs_used, uint32_t(ctx->subs[size_t(s)].size()));
             if (ctx->chan.fic_enabled) vb.add(774u, uint32_t(ctx->P.nb_cifs));
             for (const SubHost& h : ctx->subs[size_t(s)]) if (h.active) vb.add(uint32_t(h.sched.total_steps()), uint32_t(ctx->P.nb_cifs));
         }
@@ -839,7 +849,7 @@ static int chan_decode_body(dabgpu_ctx* ctx, int first, int n) {
         vb.max_steps = ctx->vl_cache.max_steps;
         if ((rc = launch_viterbi(ctx, ctx->d_jobs.as<VitJobDev>(), int(total), &vb, count_plan != nullptr))) return rc;
     }
-    if ((rc = dabplus_run(ctx->dabplus, ctx->chan, first, n, ctx->stream, &ctx->launches, ctx->prof))) return rc;
+    if ((rc = dabplus_run(ctx->dabplus, ctx->chan, first, n, ctx->vl_cache.max_subs_used, ctx->num_sms, ctx->stream, &ctx->launches, ctx->prof))) return rc;
     ctx->prof.begin(PROF_CHAN_MISC, ctx->stream);
     k_chan_finish<<<n, 32, 0, ctx->stream>>>(ctx->chan, first, n);
     ctx->prof.end(ctx->stream);
@@ -964,7 +974,7 @@ int dabgpu_fic_decode(dabgpu_ctx* ctx, const int8_t* soft_host, int n_groups, ui
     CUDA_TRY(join_dabplus(ctx));
     int rc;
     const size_t n = size_t(n_groups);
-    if ((rc = ctx->d_vsoft.alloc(n * 2304 + 16))) return rc;
+    if ((rc = ctx->d_vsoft.alloc(n * 2304 + 1024))) return rc;
     if ((rc = ctx->d_vout.alloc(n * (FIC_GROUP_BYTES + 4) + 16))) return rc;
     if ((rc = ctx->d_jobs.alloc(n * sizeof(VitJobDev)))) return rc;
     std::vector<VitJobDev> hj(n);
@@ -1203,8 +1213,15 @@ int dabgpu_ofdm_pop_frames(dabgpu_ctx* ctx, int stream, int8_t* frames_host, int
     int n = 0;
     while (popped < written && n < max_frames) {
         const size_t slot = popped & uint32_t(ctx->frame_slots - 1);
-        if (frames_host)
-            CUDA_TRY(cudaMemcpy(frames_host + size_t(n) * fb, ctx->d_frames.as<int8_t>() + (size_t(stream) * ctx->frame_slots + slot) * fb, fb, cudaMemcpyDeviceToHost));
+        if (frames_host) {
+            if ((rc = ctx->d_popstage.alloc(fb))) return rc;
+            k_frame_convert<<<dim3(16, 1), 256, 0, ctx->stream>>>(ctx->d_popstage.as<int8_t>(), fb, ctx->d_frames.as<int8_t>() + size_t(stream) * ctx->frame_slots * fb,
+                                                               size_t(ctx->frame_slots) * fb, nullptr, 0, 0u, uint32_t(slot), ctx->chan.geom, 0);
+            ctx->launches++;
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(frames_host + size_t(n) * fb, ctx->d_popstage.p, fb, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
         if (infos)
             CUDA_TRY(cudaMemcpy(infos + n, ctx->d_frame_info.as<dabgpu_frame_info>() + size_t(stream) * ctx->frame_slots + slot, sizeof(dabgpu_frame_info), cudaMemcpyDeviceToHost));
         popped++;

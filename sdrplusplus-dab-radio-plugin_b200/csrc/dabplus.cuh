@@ -327,15 +327,8 @@ __device__ void dp_process_frame(DpShared& sh, const uint8_t* __restrict__ buf, 
     }
 }
 
-__global__ void __launch_bounds__(DP_WARPS * 32)
-k_dabplus(const ChanDev C, const DabPlusDev D, const int first_stream, const int n_streams) {
-    __shared__ DpShared sh;
-    dp_load_shared(sh);
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t wid = blockIdx.x * DP_WARPS + (threadIdx.x >> 5);
-    const uint32_t si = wid / C.max_subs, sub = wid - si * C.max_subs;
-    if (si >= uint32_t(n_streams)) return;
-    const uint32_t s = uint32_t(first_stream) + si;
+// One (stream, sub-channel) work item, executed by a full warp.
+__device__ void dp_work_item(DpShared& sh, const ChanDev& C, const DabPlusDev& D, const uint32_t s, const uint32_t sub, const uint32_t lane) {
     const size_t idx = size_t(s) * C.max_subs + sub;
     if (lane == 0) D.n_events[idx] = 0;
     if (!C.status[2 * s] || sub >= C.n_subs[s]) return;
@@ -354,6 +347,22 @@ k_dabplus(const ChanDev C, const DabPlusDev D, const int first_stream, const int
                          &n_ev_local, C.counters, lane);
     }
     if (lane == 0) { D.st[idx] = st; D.n_events[idx] = n_ev_local; }
+}
+
+// Persistent CTAs: the field / CRC tables are staged in shared memory once per CTA, then its warps walk the (stream, sub-channel)
+// items.  subs_per_stream = largest sub-channel count of the streams in the call (the table has max_subs = 64 rows per stream, a
+// full ensemble uses 18: launching a warp per table row spent most of the kernel on CTAs that only loaded the tables).
+__global__ void __launch_bounds__(DP_WARPS * 32)
+k_dabplus(const ChanDev C, const DabPlusDev D, const int first_stream, const int n_streams, const uint32_t subs_per_stream) {
+    __shared__ DpShared sh;
+    dp_load_shared(sh);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t total = uint32_t(n_streams) * subs_per_stream;
+    for (uint32_t wid = blockIdx.x * DP_WARPS + (threadIdx.x >> 5); wid < total; wid += gridDim.x * DP_WARPS) {
+        const uint32_t si = wid / subs_per_stream, sub = wid - si * subs_per_stream;
+        dp_work_item(sh, C, D, uint32_t(first_stream) + si, sub, lane);
+        __syncwarp();
+    }
 }
 
 // Stand-alone AAC_Frame_Processor objects (the C++ adapter of the same name): one warp, one logical frame per call.
@@ -428,10 +437,13 @@ static int dabplus_reset_stream(DabPlusState& S, int stream) {
     return DABGPU_OK;
 }
 
-static int dabplus_run(DabPlusState& S, const ChanDev& C, int first, int n, cudaStream_t stream, uint64_t* launches, Profiler& pf) {
-    const uint32_t warps = uint32_t(n) * uint32_t(S.max_subs);
+static int dabplus_run(DabPlusState& S, const ChanDev& C, int first, int n, uint32_t subs_per_stream, int num_sms, cudaStream_t stream, uint64_t* launches,
+                       Profiler& pf) {
+    if (subs_per_stream == 0) return DABGPU_OK;
+    const uint32_t warps = uint32_t(n) * subs_per_stream;
+    const uint32_t ctas = std::min((warps + DP_WARPS - 1) / DP_WARPS, uint32_t(num_sms) * 8u);
     pf.begin(PROF_DABPLUS, stream);
-    k_dabplus<<<(warps + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, 0, stream>>>(C, S.dev, first, n);
+    k_dabplus<<<ctas, DP_WARPS * 32, 0, stream>>>(C, S.dev, first, n, subs_per_stream);
     pf.end(stream);
     (*launches)++;
     CUDA_TRY(cudaGetLastError());

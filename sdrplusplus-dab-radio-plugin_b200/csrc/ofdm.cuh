@@ -23,6 +23,7 @@
 // buffer (which, while acquiring, is not always contiguous with the stream: circular_buffer.h quirk).
 #pragma once
 #include "common.cuh"
+#include "viterbi.cuh"   // GatherGeom / frame_convert_group: layout of the soft-bit frame ring
 
 enum { OST_FINDING_NULL = 0, OST_READING_NULL_PRS = 1, OST_COARSE = 2, OST_FINE_TIME = 3, OST_READING_SYMBOLS = 4 };
 
@@ -83,6 +84,7 @@ struct OfdmDev {
     dabgpu_frame_info* frame_info;   // [stream][slot]
     uint32_t slot_mask;
     unsigned long long* counters;
+    GatherGeom fg;               // frame ring layout (planar MSC, viterbi.cuh)
 };
 
 __device__ __forceinline__ float2 cmulf(const float2 a, const float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -628,10 +630,10 @@ __global__ void k_ofdm_gather_latest(const OfdmDev D, const int first_stream, in
     if (blockIdx.x == 0 && threadIdx.x == 0) produced[blockIdx.y] = has ? 1 : 0;
     if (!has) return;
     const uint32_t slot = (D.frames_written[s] - 1u) & D.slot_mask;
-    const uint4* src = reinterpret_cast<const uint4*>(D.frames + (size_t(s) * (D.slot_mask + 1u) + slot) * D.g.frame_bits);
-    uint4* dst = reinterpret_cast<uint4*>(stage + size_t(blockIdx.y) * D.g.frame_bits);
-    const int n16 = D.g.frame_bits / 16;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
+    const int8_t* src = D.frames + (size_t(s) * (D.slot_mask + 1u) + slot) * D.g.frame_bits;
+    int8_t* dst = stage + size_t(blockIdx.y) * D.g.frame_bits;   // natural order, as the observers of On_OFDM_Frame see it
+    const uint32_t n16 = uint32_t(D.g.frame_bits) / 16u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) frame_convert_group(src, dst, i, D.fg, false);
 }
 
 // OFDM_Demod::GetFrameFFT (ofdm_demodulator.h:135, filled by PipelineThread, ofdm_demodulator.cpp:673-700): the spectra of the

@@ -21,6 +21,12 @@
 //   * DQPSK therefore needs no spectrum buffer: X_{l-1} is simply the register copy kept from the previous
 //     iteration.  Soft bits are scattered (frequency de-interleaver) into a 2K-byte shared row and leave with
 //     16-byte coalesced stores.
+//   * Frame layout in the ring (common.cuh: frame layout): the FIC symbols in natural order, every CIF of the MSC as 16 PLANES
+//     (plane r = the soft bits whose index inside the CIF is r modulo 16).  The time de-interleaver takes bit i of a logical
+//     frame from the CIF that is 15 - bitrev4(i mod 16) CIFs old (cif_deinterleaver.cpp:8-11, 62-68), so with planes every
+//     Viterbi job reads 16 contiguous runs instead of every 16th byte of 16 rows.  A data symbol is a whole number of 16-bit
+//     groups, so it contributes one contiguous run of 2K/16 bytes to each plane: the shared row is filled plane-major and the
+//     stores stay coalesced.
 #pragma once
 #include "ofdm.cuh"
 
@@ -64,6 +70,10 @@ template <int N, int FMT> struct DemodCfg {
     static constexpr int R1 = (N == 2048 || N == 256) ? 4 : (N == 1024 ? 2 : 1);
     static constexpr int NA = N + N / 8;                            // DEMOD_PADA extent
     static constexpr int NB = 11 * N / 8;                           // DEMOD_L3 extent
+    static constexpr int FIC_SYMS = (N == 256) ? 8 : 3;               // dab_parameters.h:26-90
+    static constexpr int SYMS_PER_CIF = 55296 / (2 * K);
+    static constexpr int RUN = 2 * K / 16;                            // bytes one data symbol adds to every plane of its CIF
+    static constexpr int CH = (RUN % 16 == 0) ? 16 : 8;               // store granularity (mode III: runs of 24 bytes)
     static constexpr int STAGE = ((TSYM * BPS + 15 + 15) / 16) * 16;   // one symbol + alignment slack
     static constexpr int WARPS = (T + 31) / 32;
     static constexpr size_t SMEM = size_t(NA + NB) * 8 + size_t(2 * K) + 2 * size_t(STAGE) + 16 /*mbarriers*/ + size_t(WARPS) * 8 + 16;
@@ -172,6 +182,10 @@ k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) 
         dc_thread = (v.x & 0xFFFFu) == 0xFFFFu;
         op[0] = dc_thread ? (v.y >> 16) : (v.x & 0xFFFFu);
         op[1] = v.x >> 16; op[2] = v.y & 0xFFFFu; op[3] = v.z >> 16; op[4] = v.w & 0xFFFFu; op[5] = v.w >> 16;
+        // low half: position in a natural-order row (FIC symbols); high half: position in a plane-major row (MSC symbols), where
+        // bit b of the symbol sits at (b mod 16) * RUN + b / 16.  The second bit of a carrier is K positions later, K = 0 mod 16.
+#pragma unroll
+        for (int k = 0; k < 6; k++) op[k] |= ((op[k] & 15u) * uint32_t(C::RUN) + (op[k] >> 4)) << 16;
     }
     float nf[8];
 #pragma unroll
@@ -334,23 +348,40 @@ k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) 
             // 1e-6 guard so that the dominant component truncates to exactly +-127 with the approximate reciprocal.
             const float2 pa[6] = {dc_thread ? prev[3] : prev[0], prev[1], prev[2], prev[5], prev[6], prev[7]};
             const float2 xb[6] = {dc_thread ? x[3] : x[0], x[1], x[2], x[5], x[6], x[7]};
+            const bool msc = (l - 1) >= C::FIC_SYMS;
+            const uint32_t sel = msc ? 0x4432u : 0x4410u;            // which half of op[]
+            const uint32_t second = msc ? uint32_t(K / 16) : uint32_t(K);
 #pragma unroll
             for (int k = 0; k < 6; k++) {
                 const float2 a = pa[k], b = xb[k];
                 const float vr = a.x * b.x + a.y * b.y;
                 const float vi = a.y * b.x - a.x * b.y;
                 const float sc = __fdividef(127.00012f, fmaxf(fabsf(vr), fabsf(vi)));
-                s_out[op[k]] = uint8_t(int(vr * -sc));
-                s_out[K + op[k]] = uint8_t(int(vi * sc));
+                const uint32_t pos = __byte_perm(op[k], 0u, sel);
+                s_out[pos] = uint8_t(int(vr * -sc));
+                s_out[pos + second] = uint8_t(int(vi * sc));
             }
         }
 #pragma unroll
         for (int k = 0; k < 8; k++) prev[k] = x[k];
         __syncthreads();   // (4) s_out complete; sA/sB/s_part free for the next symbol
         if (l > l0) {
-            const uint4* src = reinterpret_cast<const uint4*>(s_out);
-            uint4* dst = reinterpret_cast<uint4*>(out_frame + size_t(l - 1) * 2u * K);
-            for (int i = tid; i < 2 * K / 16; i += T) dst[i] = src[i];
+            const int m = l - 1;
+            if (m < C::FIC_SYMS) {
+                const uint4* src = reinterpret_cast<const uint4*>(s_out);
+                uint4* dst = reinterpret_cast<uint4*>(out_frame + size_t(m) * 2u * K);
+                for (int i = tid; i < 2 * K / 16; i += T) dst[i] = src[i];
+            } else {
+                // 16 runs of RUN bytes, one per plane of the symbol's CIF
+                const int cif = (m - C::FIC_SYMS) / C::SYMS_PER_CIF, q = (m - C::FIC_SYMS) - cif * C::SYMS_PER_CIF;
+                int8_t* base = out_frame + size_t(C::FIC_SYMS) * 2u * K + size_t(cif) * 55296u + size_t(q) * C::RUN;
+                constexpr int PER_RUN = C::RUN / C::CH;
+                for (int i = tid; i < 2 * K / C::CH; i += T) {
+                    const int run = i / PER_RUN, j = i - run * PER_RUN;
+                    if (C::CH == 16) *reinterpret_cast<uint4*>(base + run * 3456 + j * 16) = reinterpret_cast<const uint4*>(s_out)[i];
+                    else *reinterpret_cast<uint2*>(base + run * 3456 + j * 8) = reinterpret_cast<const uint2*>(s_out)[i];
+                }
+            }
             // s_out is rewritten only after barrier (3) of the next iteration
         }
     }

@@ -243,6 +243,12 @@ static int ofdm_init(OfdmState& O, const dabgpu_config& cfg, const dabgpu_params
     D.frame_info = d_frame_info;
     D.slot_mask = uint32_t(frame_slots - 1);
     D.counters = d_counters;
+    D.fg.nb_cifs = uint32_t(P.nb_cifs);
+    D.fg.cif_shift = (P.nb_cifs == 4) ? 2u : (P.nb_cifs == 2 ? 1u : 0u);
+    D.fg.frame_bits = uint32_t(P.nb_frame_bits);
+    D.fg.fic_bits = uint32_t(P.nb_fic_bits);
+    D.fg.cif_bits = uint32_t(P.nb_cif_bits);
+    D.fg.slot_mask = uint32_t(frame_slots - 1);
     return DABGPU_OK;
 }
 

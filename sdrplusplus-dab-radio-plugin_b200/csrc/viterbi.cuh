@@ -43,6 +43,11 @@ struct __align__(16) VitJobDev {
     uint32_t pad_;
 };
 
+// Frame layout in the soft-bit ring: [FIC, natural order, fic_bits][CIF 0][CIF 1]...; every CIF is stored as 16 planes of
+// cif_bits/16 bytes, plane r = the soft bits with index r modulo 16 inside the CIF (written that way by k_ofdm_demod2 and
+// k_frame_planarize).  Sub-channels start at multiples of 64 bits, so bit j of a sub-channel is byte (start_bit + j) / 16 of plane
+// j mod 16 -- and j mod 16 is what selects the CIF in the time de-interleaver.
+#define FRAME_PLANES 16u
 struct GatherGeom {
     uint32_t cif_shift;      // log2(CIFs per transmission frame): 2, 0, 0, 1 for modes I..IV
     uint32_t nb_cifs;        // CIFs per transmission frame
@@ -51,6 +56,48 @@ struct GatherGeom {
     uint32_t cif_bits;
     uint32_t slot_mask;      // frame ring depth - 1
 };
+__host__ __device__ __forceinline__ uint32_t geom_plane_stride(const GatherGeom& G) { return G.cif_bits / FRAME_PLANES; }
+
+// Natural-order frames (what On_OFDM_Frame observers and BasicRadio::Process see) <-> the ring layout.  One thread per group of 16
+// consecutive soft bits: in the MSC they are one byte of each plane (a warp touches 32 consecutive bytes of every plane), in the
+// FIC they stay together.  to_ring: natural -> ring, else ring -> natural.
+__device__ __forceinline__ void frame_convert_group(const int8_t* __restrict__ src, int8_t* __restrict__ dst, const uint32_t grp, const GatherGeom& G, const bool to_ring) {
+    const uint32_t i0 = grp * 16u;
+    if (i0 < G.fic_bits) {
+        *reinterpret_cast<uint4*>(dst + i0) = *reinterpret_cast<const uint4*>(src + i0);
+        return;
+    }
+    const uint32_t m = i0 - G.fic_bits, c = m / G.cif_bits, b = m - c * G.cif_bits;
+    const uint32_t pbase = G.fic_bits + c * G.cif_bits + (b >> 4), ps = geom_plane_stride(G);
+    if (to_ring) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + i0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (uint32_t r = 0; r < 16u; r++) dst[pbase + r * ps] = int8_t((w[r >> 2] >> (8u * (r & 3u))) & 0xFFu);
+    } else {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (uint32_t r = 0; r < 16u; r++) w[r >> 2] |= uint32_t(uint8_t(src[pbase + r * ps])) << (8u * (r & 3u));
+        *reinterpret_cast<uint4*>(dst + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// One frame per blockIdx.y.  nat: natural-order frames, frame y at nat + y * nat_stride.  ring: the frame ring of stream
+// first_stream (stream y at + y * stream_stride); the slot is slot_of[first_stream + y] & slot_mask (+ slot_delta), or fixed_slot
+// when slot_of is null.
+__global__ void k_frame_convert(int8_t* __restrict__ nat, const size_t nat_stride, int8_t* __restrict__ ring, const size_t stream_stride,
+                                const uint32_t* __restrict__ slot_of, const int first_stream, const uint32_t slot_delta, const uint32_t fixed_slot,
+                                const GatherGeom G, const int to_ring) {
+    const uint32_t y = blockIdx.y;
+    const uint32_t slot = slot_of ? ((slot_of[first_stream + y] + slot_delta) & G.slot_mask) : fixed_slot;
+    int8_t* fr = ring + size_t(y) * stream_stride + size_t(slot) * G.frame_bits;
+    int8_t* nt = nat + size_t(y) * nat_stride;
+    const uint32_t n_grp = G.frame_bits / 16u;
+    for (uint32_t grp = blockIdx.x * blockDim.x + threadIdx.x; grp < n_grp; grp += gridDim.x * blockDim.x) {
+        if (to_ring) frame_convert_group(nt, fr, grp, G, true);
+        else frame_convert_group(fr, nt, grp, G, false);
+    }
+}
 
 #define VIT_MAX_ERROR 1016
 #define VIT_NONSTART 5080u
@@ -59,22 +106,22 @@ struct GatherGeom {
 // renormalisation threshold inside the chunk: the per-step check can be skipped without changing results.
 #define VIT_CHUNK_SAFE (VIT_RENORM - 32u * 1020u)
 
-// Per-trellis gather table: s_rowoff[r] is the offset (relative to J.src) of the CIF row that holds the soft bits whose
-// index is r modulo 16, so a soft bit is fetched from J.src[s_rowoff[idx & 15] + idx].  Bit i of the oldest complete logical
-// frame was sent 15 - T[i mod 16] CIFs before the newest one, and the interleaver sequence T = {0,8,4,12,...} is the 4-bit
-// reversal of i (cif_deinterleaver.cpp:8-11, 62-68).  Linear jobs (no time de-interleaver) get an all-zero table.
+// Offset (relative to the stream's frame ring) of the plane that holds the soft bits with index r modulo 16 of the logical frame a
+// gather job decodes, at the first byte of its sub-channel.  Bit i of the oldest complete logical frame was sent 15 - T[i mod 16]
+// CIFs before the newest one, and the interleaver sequence T = {0,8,4,12,...} is the 4-bit reversal of i
+// (cif_deinterleaver.cpp:8-11, 62-68).
+__device__ __forceinline__ uint32_t vit_plane_offset(const uint32_t newest_cif, const uint32_t sub_start_bit, const GatherGeom& G, const uint32_t r) {
+    const uint32_t age = 15u - (__brev(r) >> 28);
+    const uint32_t cabs = newest_cif - age;
+    const uint32_t fr = cabs >> G.cif_shift;
+    const uint32_t c = cabs & (G.nb_cifs - 1u);
+    return (fr & G.slot_mask) * G.frame_bits + G.fic_bits + c * G.cif_bits + r * geom_plane_stride(G) + (sub_start_bit >> 4);
+}
+
+// Per-trellis gather table: punctured symbol idx of a gather job is J.src[s_rowoff[idx & 15] + (idx >> 4)]; linear jobs (no time
+// de-interleaver: FIC, dabgpu_viterbi_decode) read J.src[idx] (all-zero table, shift 0).
 __device__ __forceinline__ void vit_fill_rowoff(const VitJobDev& J, const GatherGeom& G, uint32_t* s_rowoff, const uint32_t lane) {
-    if (lane < 16u) {
-        uint32_t off = 0;
-        if (J.flags & VJ_GATHER) {
-            const uint32_t age = 15u - (__brev(lane) >> 28);
-            const uint32_t cabs = J.newest_cif - age;
-            const uint32_t fr = cabs >> G.cif_shift;
-            const uint32_t c = cabs & (G.nb_cifs - 1u);
-            off = (fr & G.slot_mask) * G.frame_bits + G.fic_bits + c * G.cif_bits + J.sub_start_bit;
-        }
-        s_rowoff[lane] = off;
-    }
+    if (lane < 16u) s_rowoff[lane] = (J.flags & VJ_GATHER) ? vit_plane_offset(J.newest_cif, J.sub_start_bit, G, lane) : 0u;
 }
 
 // Depuncture on the fly: mother-code symbols of trellis step t packed as 4 int8 (punctured => 0).
@@ -90,12 +137,13 @@ __device__ __forceinline__ uint32_t vit_load_step(const VitJobDev& J, const uint
     const uint32_t cnt = (c_pi_cnt[pi] >> (4u * g)) & 0xFu;
     const uint32_t pre = uint32_t(c_pi_pref[pi] >> (8u * g)) & 0xFFu;
     const uint32_t base = inb + q * c_pi_K[pi] + pre;
+    const uint32_t sh = (J.flags & VJ_GATHER) ? 4u : 0u;
     uint32_t w = 0;
 #pragma unroll
     for (uint32_t r = 0; r < 4; r++) {
         if (r < cnt) {
             const uint32_t idx = base + r;
-            w |= uint32_t(uint8_t(__ldg(J.src + (size_t(s_rowoff[idx & 15u]) + idx)))) << (8u * r);
+            w |= uint32_t(uint8_t(__ldg(J.src + (size_t(s_rowoff[idx & 15u]) + (idx >> sh))))) << (8u * r);
         }
     }
     return w;

@@ -9,8 +9,8 @@
 //   k_vit_count    histogram of the active trellises by length class (dabgpu_chan_decode takes it in k_chan_build_jobs instead)
 //   k_vit_plan     one thread: decides lanes vs warps, orders the classes longest first, assigns symbol rows
 //   k_vit_scatter  job indices grouped by class (32 consecutive entries = one warp's trellises)
-//   k_vit_prep     time de-interleave + de-puncture (the loader of viterbi.cuh with the puncturing segment cached per trellis)
-//                  into a [step][lane] word matrix per group, so that the decoder reads one coalesced 128-byte row per step
+//   k_vit_prep     time de-interleave + de-puncture into a [step][lane] word matrix per group (one lane per trellis, like the
+//                  decoder), so that the decoder reads one coalesced 128-byte row per step
 //   k_viterbi_lanes  persistent warps: forward pass (decisions to a per-warp scratch, 256 B coalesced per step), traceback,
 //                  energy dispersal, FIB CRC
 #pragma once
@@ -97,105 +97,199 @@ __device__ __forceinline__ void vl_locate(const VlPlan* __restrict__ plan, const
     row0 = plan->row_base[b] + gi * vl_bucket_rows(b);
 }
 
-// Per-trellis puncturing state of k_vit_prep: the segment that contains the first step of the current 32-step chunk, with its
-// tables, so that the common case (the whole chunk inside one segment) costs a dozen instructions per step instead of the
-// segment search and table lookups of vit_load_step.
+// ---------------------------------------------------------------------------------------------------------------------------
+// k_vit_prep: time de-interleave (CIF_Deinterleaver, cif_deinterleaver.cpp:20-71) + de-puncture (DAB_Viterbi_Decoder::
+// depuncture_symbols, dab_viterbi_decoder.cpp:131-181) of a whole call into the [step][lane] symbol matrix the decoder reads.
+//
+// One warp per group, one LANE per trellis -- the same mapping as the decoder, so a warp stores whole 128-byte rows of the
+// matrix.  Every lane keeps a window of 512 consecutive punctured symbols of its trellis in shared memory, in logical order,
+// as a ring of two UNITS of 256 symbols.  Positions are counted in a per-trellis coordinate whose multiples of 256 are 16-byte
+// aligned in memory (gather jobs: position + sub_start_bit, i.e. plane byte * 16 + plane; linear jobs: the byte address).
+//   A. refill (when the next VP_TILE steps may reach beyond the window): one unit = one 16-byte piece of each of the 16 planes of
+//      the planar frame layout (viterbi.cuh) -- 16 independent LDG.128 per lane, each piece of the frame ring is read exactly once
+//      -- turned into logical order by 4x4 byte transposes (8 PRMT per 16 bytes) and stored [word][lane] (bank = lane).  Linear
+//      jobs (FIC, dabgpu_viterbi_decode) copy 16 consecutive pieces instead.
+//   B. de-puncture, one code period of 8 steps at a time, branch-free: the kept-symbol counts and offsets of the period come
+//      from the code's two shift registers, a step's word is two LDS.32 + a funnel shift + a mask, and goes straight to the matrix.
+// The previous version fetched single bytes through the 16-way strided gather of a natural-order frame (one dependent L2 round
+// trip per step, 63 instructions per step and lane, every DRAM sector read six times).
+// ---------------------------------------------------------------------------------------------------------------------------
+#define VP_TILE 64u
+#define VP_WARPS 4u
+#define VP_WORDS 128u          // window of 512 symbols per lane
+#define VP_SMEM_BYTES (size_t(VP_WARPS) * VP_WORDS * 32u * sizeof(uint32_t))
+
+// puncturing state of one trellis: the segment that contains the current step
 struct PrepSeg { uint32_t seg, seg_end, start, inb, cntw, K, pref_lo, pref_hi; };
-__device__ __forceinline__ void prep_seg_load(PrepSeg& S, const VitJobDev& J, const uint32_t seg) {
-    const uint32_t pi = J.seg_pi[seg];
+__device__ __forceinline__ void prep_seg_load(PrepSeg& S, const VitJobDev* __restrict__ J, const uint32_t seg) {
+    const uint32_t pi = J->seg_pi[seg];
     S.seg = seg;
-    S.seg_end = J.seg_step_end[seg];
-    S.start = seg ? J.seg_step_end[seg - 1u] : 0u;
-    S.inb = J.seg_in_base[seg];
+    S.seg_end = J->seg_step_end[seg];
+    S.start = seg ? J->seg_step_end[seg - 1u] : 0u;
+    S.inb = J->seg_in_base[seg];
     S.cntw = c_pi_cnt[pi];
     S.K = c_pi_K[pi];
     S.pref_lo = uint32_t(c_pi_pref[pi]);
     S.pref_hi = uint32_t(c_pi_pref[pi] >> 32);
 }
+// index of the first punctured symbol of step t (t inside the segment)
+__device__ __forceinline__ uint32_t prep_in_index(const PrepSeg& S, const uint32_t t) {
+    const uint32_t u = t - S.start, g8 = u & 7u;
+    const uint32_t pre = (((g8 & 4u) ? S.pref_hi : S.pref_lo) >> (8u * (g8 & 3u))) & 0xFFu;
+    return S.inb + (u >> 3) * S.K + pre;
+}
 
-// One CTA per group; warp w fills the columns VP_JPW*w .. VP_JPW*w + VP_JPW-1 of the group's symbol matrix, lane = trellis
-// step within a chunk of 32.  The pass is a chain of dependent L2 round trips per warp (one per trellis and chunk: the byte
-// loads of a step are predicated on its puncturing count), so fewer trellises per warp shorten it, while more trellises
-// per warp give full-sector stores.  Measured per 256-stream step (planning kernels included): 8 per warp 0.294 ms,
-// 4 per warp 0.218 ms, 2 per warp 0.252 ms, 1 per warp 0.303 ms.
-#define VP_JPW 4u
-#define VP_WARPS (32u / VP_JPW)
+__device__ __forceinline__ void prep_transpose4(const uint32_t a, const uint32_t b, const uint32_t c, const uint32_t d, uint32_t (&o)[4]) {
+    const uint32_t t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(a, b, 0x7362);
+    const uint32_t t2 = __byte_perm(c, d, 0x5140), t3 = __byte_perm(c, d, 0x7362);
+    o[0] = __byte_perm(t0, t2, 0x5410); o[1] = __byte_perm(t0, t2, 0x7632);
+    o[2] = __byte_perm(t1, t3, 0x5410); o[3] = __byte_perm(t1, t3, 0x7632);
+}
+
+// the word of one step: `cnt` symbols from window position lam (counted in the lane's coordinate), the rest zero (punctured)
+__device__ __forceinline__ uint32_t prep_word(const uint32_t (*L)[32], const uint32_t lane, const uint32_t lam, const uint32_t cnt) {
+    const uint32_t wi = lam >> 2;
+    const uint32_t lo32 = L[wi & (VP_WORDS - 1u)][lane], hi32 = L[(wi + 1u) & (VP_WORDS - 1u)][lane];
+    // mask of cnt bytes, cnt = 0..4: the clamped funnel shift gives 0 for a shift of 32
+    return __funnelshift_r(lo32, hi32, (lam & 3u) * 8u) & __funnelshift_rc(0xFFFFFFFFu, 0u, 32u - 8u * cnt);
+}
+
 __global__ void __launch_bounds__(VP_WARPS * 32)
 k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, const uint32_t* __restrict__ list, uint32_t* __restrict__ sym, const GatherGeom G) {
-    __shared__ VitJobDev sJ[32];
-    __shared__ uint32_t s_rowoff[32][16];
-    __shared__ PrepSeg sSeg[32];
-    const uint32_t g = blockIdx.x;
+    extern __shared__ __align__(16) uint32_t s_log_raw[];     // [VP_WARPS][VP_WORDS][32]
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint32_t g = blockIdx.x * VP_WARPS + w;
     if (g >= plan->n_groups) return;
     uint32_t list0, n_in, row0;
     vl_locate(plan, g, list0, n_in, row0);
-    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    if (threadIdx.x < 32u) {
-        if (threadIdx.x < n_in) {
-            sJ[threadIdx.x] = jobs[list[list0 + threadIdx.x]];
-            uint32_t seg = 0;
-            while (seg < DABGPU_MAX_SEGMENTS - 1u && sJ[threadIdx.x].seg_step_end[seg] == 0u) seg++;   // skip empty leading segments
-            prep_seg_load(sSeg[threadIdx.x], sJ[threadIdx.x], seg);
+    const bool have = lane < n_in;
+    const VitJobDev* __restrict__ J = jobs + (have ? list[list0 + lane] : 0u);
+    const uint32_t N = have ? J->total_steps : 0u;
+    const bool gather = have && (J->flags & VJ_GATHER) != 0u;
+    const uint32_t steps_g = __reduce_max_sync(FULL_MASK, N);
+    const uint32_t padded = ((steps_g + VL_UNROLL - 1u) / VL_UNROLL) * VL_UNROLL + VL_UNROLL;
+    uint32_t (*L)[32] = reinterpret_cast<uint32_t (*)[32]>(s_log_raw + size_t(w) * VP_WORDS * 32u);
+    // memory of the unit u: gather jobs -- plane r at base + poff[r] + 16 * u; linear jobs -- base + 256 * u
+    const uint8_t* base = nullptr;
+    uint32_t poff[16];
+    uint32_t origin = 0;                     // lane coordinate of the punctured symbol 0
+#pragma unroll
+    for (uint32_t r = 0; r < 16u; r++) poff[r] = 0u;
+    if (have) {
+        if (gather) {
+            base = reinterpret_cast<const uint8_t*>(J->src);
+            origin = J->sub_start_bit;
+#pragma unroll
+            for (uint32_t r = 0; r < 16u; r++) poff[r] = vit_plane_offset(J->newest_cif, 0u, G, r);
         } else {
-            sJ[threadIdx.x].total_steps = 0u;
-            sSeg[threadIdx.x].seg_end = 0u;   // never on the fast path
+            const uintptr_t a = reinterpret_cast<uintptr_t>(J->src);
+            base = reinterpret_cast<const uint8_t*>(a & ~uintptr_t(255));
+            origin = uint32_t(a & 255u);
         }
     }
-    __syncthreads();
-    uint32_t steps_g = sJ[lane].total_steps;
-    steps_g = __reduce_max_sync(FULL_MASK, steps_g);
-    const uint32_t padded = ((steps_g + VL_UNROLL - 1u) / VL_UNROLL) * VL_UNROLL + VL_UNROLL;
-#pragma unroll 1
-    for (uint32_t jj = 0; jj < VP_JPW; jj++) {
-        const uint32_t q = VP_JPW * w + jj;
-        if (sJ[q].total_steps != 0u) vit_fill_rowoff(sJ[q], G, s_rowoff[q], lane);
+    PrepSeg S;
+    S.seg_end = 0u; S.start = 0u; S.inb = 0u; S.cntw = 0u; S.K = 0u; S.pref_lo = 0u; S.pref_hi = 0u; S.seg = 0u;
+    bool odd = false;   // a segment that does not start on a code period (only dabgpu_viterbi_decode can build one: 128-bit blocks otherwise)
+    if (have) {
+        uint32_t seg = 0;
+        while (seg < DABGPU_MAX_SEGMENTS - 1u && J->seg_step_end[seg] == 0u) seg++;   // skip empty leading segments
+        prep_seg_load(S, J, seg);
+        for (uint32_t k = 0; k + 1u < DABGPU_MAX_SEGMENTS; k++) odd = odd || ((J->seg_step_end[k] & 7u) != 0u && J->seg_step_end[k] < N);
     }
-    __syncwarp();
-    uint32_t* dst = sym + (size_t(row0) * 32u + VP_JPW * w);
-    // Measured alternatives: a planar soft-bit layout (positions r mod 16 contiguous per CIF) removed
-    // the DRAM over-fetch of this pass (274 -> 70 MB) but not its time, and cost k_ofdm_demod 2 percent; issuing the byte loads
-    // of the 8 trellises round by round (8 in flight per lane) did not help either: the pass is bound by its instruction count
-    // (about 100 per trellis step and lane with vit_load_step), hence the cached segment state below.
+    const bool any_odd = __any_sync(FULL_MASK, odd);
+    uint32_t next_unit = have ? ((origin + S.inb) >> 8) : 0u;   // units below this one are in the window (the last two of them)
+    uint32_t* __restrict__ dst = sym + size_t(row0) * 32u + lane;
+
 #pragma unroll 1
-    for (uint32_t t0 = 0; t0 < padded; t0 += 32u) {
-        const uint32_t t = t0 + lane;
-        uint32_t v[VP_JPW];
+    for (uint32_t t0 = 0; t0 < padded; t0 += VP_TILE) {
+        // ---- A. refill: the tile reads at most 4 * VP_TILE = 256 symbols from the position of its first step ----
+        uint32_t need_unit = 0;
+        if (t0 < N) {
+            while (t0 >= S.seg_end && S.seg < DABGPU_MAX_SEGMENTS - 1u) prep_seg_load(S, J, S.seg + 1u);
+            need_unit = ((origin + prep_in_index(S, t0) + 4u * VP_TILE - 1u) >> 8) + 1u;
+        }
+        while (__any_sync(FULL_MASK, next_unit < need_unit)) {
+            if (next_unit < need_unit) {
+                const uint32_t u = next_unit++, h = (u & 1u) * 64u;
+                if (gather) {
 #pragma unroll
-        for (uint32_t jj = 0; jj < VP_JPW; jj++) {
-            const uint32_t q = VP_JPW * w + jj;
-            const PrepSeg& S = sSeg[q];
-            if (t0 + 32u <= S.seg_end) {
-                // the whole chunk lies inside the cached segment (warp-uniform test): DAB_Viterbi_Decoder::depuncture_symbols
-                // (dab_viterbi_decoder.cpp:131-181) with segment, code and tables read once per warp
-                const uint32_t u = t - S.start, g8 = u & 7u;
-                const uint32_t cnt = (S.cntw >> (4u * g8)) & 0xFu;
-                const uint32_t pre = (((g8 & 4u) ? S.pref_hi : S.pref_lo) >> (8u * (g8 & 3u))) & 0xFFu;
-                const uint32_t base = S.inb + (u >> 3) * S.K + pre;
-                const int8_t* __restrict__ src = sJ[q].src;
-                uint32_t word = 0;
+                    for (uint32_t half = 0; half < 2u; half++) {   // two batches of 8 pieces: bounds the registers in flight
+                        uint4 P[8];
 #pragma unroll
-                for (uint32_t r = 0; r < 4; r++) {
-                    if (r < cnt) {
-                        const uint32_t idx = base + r;
-                        word |= uint32_t(uint8_t(__ldg(src + (size_t(s_rowoff[q][idx & 15u]) + idx)))) << (8u * r);
+                        for (uint32_t j = 0; j < 8u; j++) P[j] = __ldg(reinterpret_cast<const uint4*>(base + (size_t(poff[8u * half + j]) + 16u * u)));
+#pragma unroll
+                        for (uint32_t mm = 0; mm < 2u; mm++) {
+                            const uint32_t m = 2u * half + mm;
+                            const uint32_t* p0 = reinterpret_cast<const uint32_t*>(&P[4u * mm + 0u]);
+                            const uint32_t* p1 = reinterpret_cast<const uint32_t*>(&P[4u * mm + 1u]);
+                            const uint32_t* p2 = reinterpret_cast<const uint32_t*>(&P[4u * mm + 2u]);
+                            const uint32_t* p3 = reinterpret_cast<const uint32_t*>(&P[4u * mm + 3u]);
+#pragma unroll
+                            for (uint32_t x = 0; x < 4u; x++) {
+                                uint32_t o[4];
+                                prep_transpose4(p0[x], p1[x], p2[x], p3[x], o);
+                                // o[kk] = the planes 4m..4m+3 at plane byte 4x + kk of the piece = symbols 16 * (4x + kk) + 4m .. + 3 of the unit
+#pragma unroll
+                                for (uint32_t kk = 0; kk < 4u; kk++) L[h + (4u * x + kk) * 4u + m][lane] = o[kk];
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (uint32_t half = 0; half < 2u; half++) {
+                        uint4 P[8];
+#pragma unroll
+                        for (uint32_t j = 0; j < 8u; j++) P[j] = __ldg(reinterpret_cast<const uint4*>(base + (size_t(u) * 256u + 128u * half + 16u * j)));
+#pragma unroll
+                        for (uint32_t j = 0; j < 8u; j++) {
+                            const uint32_t wbase = h + 32u * half + 4u * j;
+                            L[wbase + 0u][lane] = P[j].x; L[wbase + 1u][lane] = P[j].y; L[wbase + 2u][lane] = P[j].z; L[wbase + 3u][lane] = P[j].w;
+                        }
                     }
                 }
-                v[jj] = word;
-            } else {
-                v[jj] = (t < sJ[q].total_steps) ? vit_load_step(sJ[q], s_rowoff[q], t) : 0u;
             }
         }
-        if (t < padded) *reinterpret_cast<uint4*>(dst + size_t(t) * 32u) = make_uint4(v[0], v[1], v[2], v[3]);
-        // move the cached segments to the one that contains the first step of the next chunk
         __syncwarp();
-        if (lane < VP_JPW) {
-            const uint32_t q = VP_JPW * w + lane;
-            PrepSeg& S = sSeg[q];
-            if (S.seg_end != 0u && t0 + 32u >= S.seg_end && S.seg < DABGPU_MAX_SEGMENTS - 1u) {
-                uint32_t seg = S.seg;
-                while (seg < DABGPU_MAX_SEGMENTS - 1u && t0 + 32u >= sJ[q].seg_step_end[seg]) seg++;
-                prep_seg_load(S, sJ[q], seg);
+        // ---- B. de-puncture VP_TILE steps ----
+        if (any_odd) {   // general form, step by step
+#pragma unroll 1
+            for (uint32_t i = 0; i < VP_TILE; i++) {
+                const uint32_t t = t0 + i;
+                if (t >= padded) break;
+                uint32_t word = 0;
+                if (t < N) {
+                    while (t >= S.seg_end && S.seg < DABGPU_MAX_SEGMENTS - 1u) prep_seg_load(S, J, S.seg + 1u);
+                    const uint32_t g8 = (t - S.start) & 7u;
+                    word = prep_word(L, lane, origin + prep_in_index(S, t), (S.cntw >> (4u * g8)) & 0xFu);
+                }
+                dst[size_t(t) * 32u] = word;
             }
+            __syncwarp();
+            continue;
+        }
+        // one code period (8 steps) at a time: every segment starts on a period (128-bit blocks = 32 steps)
+#pragma unroll 1
+        for (uint32_t p8 = 0; p8 < VP_TILE; p8 += 8u) {
+            const uint32_t tp = t0 + p8;
+            if (tp >= padded) break;                       // warp-uniform
+            uint32_t lam = 0, cw = 0, plo = 0, phi = 0;
+            if (tp < N) {
+                while (tp >= S.seg_end && S.seg < DABGPU_MAX_SEGMENTS - 1u) prep_seg_load(S, J, S.seg + 1u);
+                lam = origin + S.inb + ((tp - S.start) >> 3) * S.K;
+                const uint32_t nv = min(N - tp, 8u);       // steps of the period that exist: the others get count 0
+                cw = S.cntw & __funnelshift_rc(0xFFFFFFFFu, 0u, 32u - 4u * nv);
+                plo = S.pref_lo; phi = S.pref_hi;
+            }
+            uint32_t words[8];
+#pragma unroll
+            for (uint32_t g8 = 0; g8 < 8u; g8++) {
+                const uint32_t cnt = (cw >> (4u * g8)) & 0xFu;
+                const uint32_t pre = ((g8 & 4u) ? (phi >> (8u * (g8 & 3u))) : (plo >> (8u * g8))) & 0xFFu;
+                words[g8] = prep_word(L, lane, lam + pre, cnt);
+            }
+#pragma unroll
+            for (uint32_t g8 = 0; g8 < 8u; g8++)
+                if (tp + g8 < padded) dst[size_t(tp + g8) * 32u] = words[g8];
         }
         __syncwarp();
     }
