@@ -41,6 +41,7 @@ struct ChanDev {
     uint8_t* fic_crc;                // [stream][nb_cifs][4]
     uint8_t* msc_out;                // [stream][nb_cifs][CIF_OUT_STRIDE]
     uint8_t* msc_valid;              // [stream][nb_cifs][max_subs]
+    int8_t* deint;                   // [stream][nb_cifs][cif_bits]: the CIFs of the frame being decoded after the time de-interleaver
     int32_t* status;                 // [stream][2] = {decoded, frame_index}
     unsigned long long* counters;    // see CNT_* below
 };
@@ -108,16 +109,15 @@ __global__ void k_chan_build_jobs(const ChanDev C, VitJobDev* __restrict__ jobs,
                 const bool valid = consumed >= 16u && cfg.total_steps != 0u;   // total_steps 0: entry removed (dabgpu_msc_remove_subchannel)
                 C.msc_valid[(size_t(s) * nb_cifs + c) * C.max_subs + sub] = valid ? 1 : 0;
                 if (valid) {
-                    J.src = ring;
+                    // the sub-channel's logical frame, already de-interleaved by k_chan_deinterleave: an ordinary linear job
+                    J.src = C.deint + (size_t(s) * nb_cifs + c) * C.geom.cif_bits + cfg.start_bit;
                     J.out = C.msc_out + (size_t(s) * nb_cifs + c) * CIF_OUT_STRIDE + cfg.out_offset;
 #pragma unroll
                     for (int i = 0; i < DABGPU_MAX_SEGMENTS; i++) { J.seg_step_end[i] = cfg.seg_step_end[i]; J.seg_in_base[i] = cfg.seg_in_base[i]; }
 #pragma unroll
                     for (int i = 0; i < 8; i++) J.seg_pi[i] = cfg.seg_pi[i];
                     J.n_seg = cfg.n_seg; J.total_steps = cfg.total_steps; J.n_out_bytes = cfg.n_out_bytes;
-                    J.flags = VJ_DESCRAMBLE | VJ_GATHER;
-                    J.newest_cif = t * nb_cifs + c;
-                    J.sub_start_bit = cfg.start_bit;
+                    J.flags = VJ_DESCRAMBLE;
                 }
             }
         }
@@ -127,6 +127,40 @@ __global__ void k_chan_build_jobs(const ChanDev C, VitJobDev* __restrict__ jobs,
         if (J.total_steps >= VL_MAX_STEPS) count_plan->oversize = 1u;
         else atomicAdd(&count_plan->count[vl_bucket(J.total_steps)], 1u);
     }
+}
+
+// CIF_Deinterleaver::Deinterleave (dab/msc/cif_deinterleaver.cpp:20-71) for the nb_cifs CIFs of the frame every stream decodes in
+// this call.  Sub-channels start at multiples of 64 bits, so the rule "bit i of a logical frame comes from the CIF that is
+// 15 - bitrev4(i mod 16) CIFs old" acts on the whole 55296-bit CIF alike, whatever the sub-channel layout: the kernel writes the
+// de-interleaved CIF in natural order and every MSC Viterbi job becomes a linear job over a piece of it.
+// One thread per capacity unit (64 soft bits = 4 bytes of each of the 16 planes of the ring layout, viterbi.cuh): 16 word loads,
+// each coalesced across the threads of a warp (128 contiguous bytes of one plane), 4x4 byte transposes in registers (32 PRMT),
+// four 16-byte stores that are contiguous across the warp as well.  grid = (ceil(cu / blockDim), streams * nb_cifs).
+__device__ __forceinline__ void deint_transpose4(const uint32_t a, const uint32_t b, const uint32_t c, const uint32_t d, uint32_t (&o)[4]) {
+    const uint32_t t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(a, b, 0x7362);
+    const uint32_t t2 = __byte_perm(c, d, 0x5140), t3 = __byte_perm(c, d, 0x7362);
+    o[0] = __byte_perm(t0, t2, 0x5410); o[1] = __byte_perm(t0, t2, 0x7632);
+    o[2] = __byte_perm(t1, t3, 0x5410); o[3] = __byte_perm(t1, t3, 0x7632);
+}
+__global__ void __launch_bounds__(288) k_chan_deinterleave(const ChanDev C, const int first_stream) {
+    const uint32_t nb_cifs = C.geom.nb_cifs;
+    const uint32_t si = blockIdx.y / nb_cifs, c = blockIdx.y - si * nb_cifs;
+    const uint32_t s = uint32_t(first_stream) + si;
+    if (!C.status[2 * s] || C.n_subs[s] == 0u) return;
+    const uint32_t cu = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cu >= C.geom.cif_bits / 64u) return;
+    const uint32_t newest = uint32_t(C.status[2 * s + 1]) * nb_cifs + c;
+    const int8_t* ring = C.frames + size_t(s) * C.stream_frames_stride;
+    uint32_t p[16];
+#pragma unroll
+    for (uint32_t r = 0; r < 16u; r++) p[r] = __ldg(reinterpret_cast<const uint32_t*>(ring + (size_t(vit_plane_offset(newest, 0u, C.geom, r)) + 4u * cu)));
+    // o[m][kk] = planes 4m..4m+3 at plane byte 4cu + kk = soft bits 64cu + 16kk + 4m .. + 3 of the logical CIF
+    uint32_t o[4][4];
+#pragma unroll
+    for (uint32_t m = 0; m < 4u; m++) deint_transpose4(p[4u * m], p[4u * m + 1u], p[4u * m + 2u], p[4u * m + 3u], o[m]);
+    uint4* dst = reinterpret_cast<uint4*>(C.deint + (size_t(s) * nb_cifs + c) * C.geom.cif_bits + 64u * cu);
+#pragma unroll
+    for (uint32_t kk = 0; kk < 4u; kk++) dst[kk] = make_uint4(o[0][kk], o[1][kk], o[2][kk], o[3][kk]);
 }
 
 // One warp per stream: advance the consumption counters after the Viterbi pass (lanes over the sub-channels).

@@ -51,6 +51,7 @@ struct dabgpu_ctx {
     DevBuf d_frames_snapshot;   // frames_written as the channel decode sees it (copied on the main stream before the fork)
     DevBuf d_subcfg, d_nsubs, d_cifs_consumed;
     DevBuf d_fic_out, d_fic_crc, d_msc_out, d_msc_valid, d_status, d_counters;
+    DevBuf d_deint;   // de-interleaved CIFs of the frame being decoded (k_chan_deinterleave)
     std::vector<std::vector<SubHost>> subs;
     ChanDev chan;
     PinnedBuf h_status, h_stage;
@@ -229,6 +230,7 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
     TRY_OR_FREE(ctx->d_fic_crc.alloc(size_t(S) * P.nb_cifs * 4));
     TRY_OR_FREE(ctx->d_msc_out.alloc(size_t(S) * P.nb_cifs * CIF_OUT_STRIDE));
     TRY_OR_FREE(ctx->d_msc_valid.alloc(size_t(S) * P.nb_cifs * ctx->max_subs));
+    TRY_OR_FREE(ctx->d_deint.alloc(size_t(S) * P.nb_cifs * P.nb_cif_bits + 1024));   // + slack: k_vit_prep reads whole 256-byte units
     TRY_OR_FREE(ctx->d_status.alloc(size_t(S) * 8));
     TRY_OR_FREE(ctx->d_counters.alloc(CNT_COUNT * 8));
     TRY_OR_FREE(ctx->h_status.alloc(size_t(S) * 8 + 4096));
@@ -274,6 +276,7 @@ int dabgpu_ctx_create(const dabgpu_config* cfg, dabgpu_ctx** out) {
     C.fic_crc = ctx->d_fic_crc.as<uint8_t>();
     C.msc_out = ctx->d_msc_out.as<uint8_t>();
     C.msc_valid = ctx->d_msc_valid.as<uint8_t>();
+    C.deint = ctx->d_deint.as<int8_t>();
     C.status = ctx->d_status.as<int32_t>();
     C.counters = ctx->d_counters.as<unsigned long long>();
 
@@ -325,7 +328,7 @@ void dabgpu_ctx_destroy(dabgpu_ctx* ctx) {
     dabplus_destroy(ctx->dabplus);
     DevBuf* bufs[] = {&ctx->d_vlplan, &ctx->d_vllist, &ctx->d_vlsym, &ctx->d_vlscratch, &ctx->d_prbs, &ctx->d_counter, &ctx->d_scratch, &ctx->d_jobs, &ctx->d_vsoft, &ctx->d_vout, &ctx->d_verr,
                       &ctx->d_frames, &ctx->d_frames_written, &ctx->d_frames_decoded, &ctx->d_frames_snapshot, &ctx->d_pushstage, &ctx->d_popstage, &ctx->d_frame_info, &ctx->d_subcfg, &ctx->d_nsubs,
-                      &ctx->d_cifs_consumed, &ctx->d_fic_out, &ctx->d_fic_crc, &ctx->d_msc_out, &ctx->d_msc_valid, &ctx->d_status,
+                      &ctx->d_cifs_consumed, &ctx->d_fic_out, &ctx->d_fic_crc, &ctx->d_msc_out, &ctx->d_msc_valid, &ctx->d_deint, &ctx->d_status,
                       &ctx->d_counters};
     for (DevBuf* b : bufs) b->release();
     ctx->h_status.release();
@@ -829,8 +832,12 @@ static int chan_decode_body(dabgpu_ctx* ctx, int first, int n) {
     ctx->prof.begin(PROF_CHAN_MISC, ctx->stream);
     if (count_plan) CUDA_TRY(cudaMemsetAsync(count_plan, 0, sizeof(VlPlan), ctx->stream));
     k_chan_build_jobs<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->chan, ctx->d_jobs.as<VitJobDev>(), first, n, count_plan);
+    {
+        const uint32_t cus = uint32_t(ctx->P.nb_cif_bits) / 64u;
+        k_chan_deinterleave<<<dim3((cus + 287u) / 288u, uint32_t(n) * uint32_t(ctx->P.nb_cifs)), 288, 0, ctx->stream>>>(ctx->chan, first);
+    }
     ctx->prof.end(ctx->stream);
-    ctx->launches++;
+    ctx->launches += 2;
     if (ctx->vl_cache.first != first || ctx->vl_cache.n != n || ctx->vl_cache.epoch != ctx->cfg_epoch) {
         VlBound vb;
         ctx->vl_cache.max_subs_used = 0;

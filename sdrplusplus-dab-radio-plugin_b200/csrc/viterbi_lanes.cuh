@@ -98,21 +98,19 @@ __device__ __forceinline__ void vl_locate(const VlPlan* __restrict__ plan, const
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// k_vit_prep: time de-interleave (CIF_Deinterleaver, cif_deinterleaver.cpp:20-71) + de-puncture (DAB_Viterbi_Decoder::
-// depuncture_symbols, dab_viterbi_decoder.cpp:131-181) of a whole call into the [step][lane] symbol matrix the decoder reads.
+// k_vit_prep: de-puncture (DAB_Viterbi_Decoder::depuncture_symbols, dab_viterbi_decoder.cpp:131-181) of a whole call into the
+// [step][lane] symbol matrix the decoder reads.  The punctured symbols of every trellis are contiguous in memory: FIC groups
+// and dabgpu_viterbi_decode jobs by nature, MSC sub-channels because k_chan_deinterleave (chan.cuh) has undone the time
+// interleaver for the whole CIF.
 //
 // One warp per group, one LANE per trellis -- the same mapping as the decoder, so a warp stores whole 128-byte rows of the
-// matrix.  Every lane keeps a window of 512 consecutive punctured symbols of its trellis in shared memory, in logical order,
-// as a ring of two UNITS of 256 symbols.  Positions are counted in a per-trellis coordinate whose multiples of 256 are 16-byte
-// aligned in memory (gather jobs: position + sub_start_bit, i.e. plane byte * 16 + plane; linear jobs: the byte address).
-//   A. refill (when the next VP_TILE steps may reach beyond the window): one unit = one 16-byte piece of each of the 16 planes of
-//      the planar frame layout (viterbi.cuh) -- 16 independent LDG.128 per lane, each piece of the frame ring is read exactly once
-//      -- turned into logical order by 4x4 byte transposes (8 PRMT per 16 bytes) and stored [word][lane] (bank = lane).  Linear
-//      jobs (FIC, dabgpu_viterbi_decode) copy 16 consecutive pieces instead.
+// matrix.  Every lane keeps a window of 512 consecutive punctured symbols of its trellis in shared memory ([word][lane], bank =
+// lane) as a ring of two units of 256 bytes (256-byte aligned in memory).
+//   A. refill, when the next VP_TILE steps may reach beyond the window: 16 independent LDG.128 per lane; each byte is read once.
 //   B. de-puncture, one code period of 8 steps at a time, branch-free: the kept-symbol counts and offsets of the period come
 //      from the code's two shift registers, a step's word is two LDS.32 + a funnel shift + a mask, and goes straight to the matrix.
-// The previous version fetched single bytes through the 16-way strided gather of a natural-order frame (one dependent L2 round
-// trip per step, 63 instructions per step and lane, every DRAM sector read six times).
+// The first version fetched single bytes through the 16-way strided gather of a natural-order frame ring (one dependent L2
+// round trip per step, 63 instructions per step and lane, every DRAM sector read six times).
 // ---------------------------------------------------------------------------------------------------------------------------
 #define VP_TILE 64u
 #define VP_WARPS 4u
@@ -139,13 +137,6 @@ __device__ __forceinline__ uint32_t prep_in_index(const PrepSeg& S, const uint32
     return S.inb + (u >> 3) * S.K + pre;
 }
 
-__device__ __forceinline__ void prep_transpose4(const uint32_t a, const uint32_t b, const uint32_t c, const uint32_t d, uint32_t (&o)[4]) {
-    const uint32_t t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(a, b, 0x7362);
-    const uint32_t t2 = __byte_perm(c, d, 0x5140), t3 = __byte_perm(c, d, 0x7362);
-    o[0] = __byte_perm(t0, t2, 0x5410); o[1] = __byte_perm(t0, t2, 0x7632);
-    o[2] = __byte_perm(t1, t3, 0x5410); o[3] = __byte_perm(t1, t3, 0x7632);
-}
-
 // the word of one step: `cnt` symbols from window position lam (counted in the lane's coordinate), the rest zero (punctured)
 __device__ __forceinline__ uint32_t prep_word(const uint32_t (*L)[32], const uint32_t lane, const uint32_t lam, const uint32_t cnt) {
     const uint32_t wi = lam >> 2;
@@ -165,27 +156,16 @@ k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, 
     const bool have = lane < n_in;
     const VitJobDev* __restrict__ J = jobs + (have ? list[list0 + lane] : 0u);
     const uint32_t N = have ? J->total_steps : 0u;
-    const bool gather = have && (J->flags & VJ_GATHER) != 0u;
     const uint32_t steps_g = __reduce_max_sync(FULL_MASK, N);
     const uint32_t padded = ((steps_g + VL_UNROLL - 1u) / VL_UNROLL) * VL_UNROLL + VL_UNROLL;
     uint32_t (*L)[32] = reinterpret_cast<uint32_t (*)[32]>(s_log_raw + size_t(w) * VP_WORDS * 32u);
-    // memory of the unit u: gather jobs -- plane r at base + poff[r] + 16 * u; linear jobs -- base + 256 * u
+    // unit u of the window = the 256 bytes at base + 256 * u; positions are counted from `base` (lane coordinate)
     const uint8_t* base = nullptr;
-    uint32_t poff[16];
     uint32_t origin = 0;                     // lane coordinate of the punctured symbol 0
-#pragma unroll
-    for (uint32_t r = 0; r < 16u; r++) poff[r] = 0u;
     if (have) {
-        if (gather) {
-            base = reinterpret_cast<const uint8_t*>(J->src);
-            origin = J->sub_start_bit;
-#pragma unroll
-            for (uint32_t r = 0; r < 16u; r++) poff[r] = vit_plane_offset(J->newest_cif, 0u, G, r);
-        } else {
-            const uintptr_t a = reinterpret_cast<uintptr_t>(J->src);
-            base = reinterpret_cast<const uint8_t*>(a & ~uintptr_t(255));
-            origin = uint32_t(a & 255u);
-        }
+        const uintptr_t a = reinterpret_cast<uintptr_t>(J->src);
+        base = reinterpret_cast<const uint8_t*>(a & ~uintptr_t(255));
+        origin = uint32_t(a & 255u);
     }
     PrepSeg S;
     S.seg_end = 0u; S.start = 0u; S.inb = 0u; S.cntw = 0u; S.K = 0u; S.pref_lo = 0u; S.pref_hi = 0u; S.seg = 0u;
@@ -211,30 +191,7 @@ k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, 
         while (__any_sync(FULL_MASK, next_unit < need_unit)) {
             if (next_unit < need_unit) {
                 const uint32_t u = next_unit++, h = (u & 1u) * 64u;
-                if (gather) {
-#pragma unroll
-                    for (uint32_t half = 0; half < 2u; half++) {   // two batches of 8 pieces: bounds the registers in flight
-                        uint4 P[8];
-#pragma unroll
-                        for (uint32_t j = 0; j < 8u; j++) P[j] = __ldg(reinterpret_cast<const uint4*>(base + (size_t(poff[8u * half + j]) + 16u * u)));
-#pragma unroll
-                        for (uint32_t mm = 0; mm < 2u; mm++) {
-                            const uint32_t m = 2u * half + mm;
-                            const uint32_t* p0 = reinterpret_cast<const uint32_t*>(&P[4u * mm + 0u]);
-                            const uint32_t* p1 = reinterpret_cast<const uint32_t*>(&P[4u * mm + 1u]);
-                            const uint32_t* p2 = reinterpret_cast<const uint32_t*>(&P[4u * mm + 2u]);
-                            const uint32_t* p3 = reinterpret_cast<const uint32_t*>(&P[4u * mm + 3u]);
-#pragma unroll
-                            for (uint32_t x = 0; x < 4u; x++) {
-                                uint32_t o[4];
-                                prep_transpose4(p0[x], p1[x], p2[x], p3[x], o);
-                                // o[kk] = the planes 4m..4m+3 at plane byte 4x + kk of the piece = symbols 16 * (4x + kk) + 4m .. + 3 of the unit
-#pragma unroll
-                                for (uint32_t kk = 0; kk < 4u; kk++) L[h + (4u * x + kk) * 4u + m][lane] = o[kk];
-                            }
-                        }
-                    }
-                } else {
+                {
 #pragma unroll
                     for (uint32_t half = 0; half < 2u; half++) {
                         uint4 P[8];
