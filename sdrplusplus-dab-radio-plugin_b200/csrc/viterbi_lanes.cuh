@@ -104,18 +104,21 @@ __device__ __forceinline__ void vl_locate(const VlPlan* __restrict__ plan, const
 // interleaver for the whole CIF.
 //
 // One warp per group, one LANE per trellis -- the same mapping as the decoder, so a warp stores whole 128-byte rows of the
-// matrix.  Every lane keeps a window of 512 consecutive punctured symbols of its trellis in shared memory ([word][lane], bank =
-// lane) as a ring of two units of 256 bytes (256-byte aligned in memory).
-//   A. refill, when the next VP_TILE steps may reach beyond the window: 16 independent LDG.128 per lane; each byte is read once.
+// matrix.  Every lane keeps a window of 256 consecutive punctured symbols of its trellis in shared memory ([word][lane], bank =
+// lane) as a ring of two units of 128 bytes (128-byte aligned in memory); the first words of the ring are repeated behind its
+// end, so that a code period (at most 32 symbols) is read without wrapping.  8.5 KB per warp: 24 warps per SM.
+//   A. refill, when the next VP_TILE steps may reach beyond the window: 8 independent LDG.128 per lane; each byte is read once.
 //   B. de-puncture, one code period of 8 steps at a time, branch-free: the kept-symbol counts and offsets of the period come
 //      from the code's two shift registers, a step's word is two LDS.32 + a funnel shift + a mask, and goes straight to the matrix.
 // The first version fetched single bytes through the 16-way strided gather of a natural-order frame ring (one dependent L2
 // round trip per step, 63 instructions per step and lane, every DRAM sector read six times).
 // ---------------------------------------------------------------------------------------------------------------------------
-#define VP_TILE 64u
+#define VP_TILE 32u
 #define VP_WARPS 4u
-#define VP_WORDS 128u          // window of 512 symbols per lane
-#define VP_SMEM_BYTES (size_t(VP_WARPS) * VP_WORDS * 32u * sizeof(uint32_t))
+#define VP_UNIT 128u           // bytes per refill
+#define VP_WORDS 64u           // window of 2 units = 256 symbols per lane
+#define VP_MIRROR 9u
+#define VP_SMEM_BYTES (size_t(VP_WARPS) * (VP_WORDS + VP_MIRROR) * 32u * sizeof(uint32_t))
 
 // puncturing state of one trellis: the segment that contains the current step
 struct PrepSeg { uint32_t seg, seg_end, start, inb, cntw, K, pref_lo, pref_hi; };
@@ -137,17 +140,17 @@ __device__ __forceinline__ uint32_t prep_in_index(const PrepSeg& S, const uint32
     return S.inb + (u >> 3) * S.K + pre;
 }
 
+// mask of cnt bytes, cnt = 0..4: the clamped funnel shift gives 0 for a shift of 32
+__device__ __forceinline__ uint32_t prep_mask(const uint32_t cnt) { return __funnelshift_rc(0xFFFFFFFFu, 0u, 32u - 8u * cnt); }
 // the word of one step: `cnt` symbols from window position lam (counted in the lane's coordinate), the rest zero (punctured)
 __device__ __forceinline__ uint32_t prep_word(const uint32_t (*L)[32], const uint32_t lane, const uint32_t lam, const uint32_t cnt) {
-    const uint32_t wi = lam >> 2;
-    const uint32_t lo32 = L[wi & (VP_WORDS - 1u)][lane], hi32 = L[(wi + 1u) & (VP_WORDS - 1u)][lane];
-    // mask of cnt bytes, cnt = 0..4: the clamped funnel shift gives 0 for a shift of 32
-    return __funnelshift_r(lo32, hi32, (lam & 3u) * 8u) & __funnelshift_rc(0xFFFFFFFFu, 0u, 32u - 8u * cnt);
+    const uint32_t wi = (lam >> 2) & (VP_WORDS - 1u);
+    return __funnelshift_r(L[wi][lane], L[wi + 1u][lane], lam * 8u) & prep_mask(cnt);   // the shift uses the low 5 bits: (lam & 3) * 8
 }
 
 __global__ void __launch_bounds__(VP_WARPS * 32)
 k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, const uint32_t* __restrict__ list, uint32_t* __restrict__ sym, const GatherGeom G) {
-    extern __shared__ __align__(16) uint32_t s_log_raw[];     // [VP_WARPS][VP_WORDS][32]
+    extern __shared__ __align__(16) uint32_t s_log_raw[];     // [VP_WARPS][VP_WORDS + VP_MIRROR][32]
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const uint32_t g = blockIdx.x * VP_WARPS + w;
     if (g >= plan->n_groups) return;
@@ -158,17 +161,21 @@ k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, 
     const uint32_t N = have ? J->total_steps : 0u;
     const uint32_t steps_g = __reduce_max_sync(FULL_MASK, N);
     const uint32_t padded = ((steps_g + VL_UNROLL - 1u) / VL_UNROLL) * VL_UNROLL + VL_UNROLL;
-    uint32_t (*L)[32] = reinterpret_cast<uint32_t (*)[32]>(s_log_raw + size_t(w) * VP_WORDS * 32u);
-    // unit u of the window = the 256 bytes at base + 256 * u; positions are counted from `base` (lane coordinate)
+    uint32_t (*L)[32] = reinterpret_cast<uint32_t (*)[32]>(s_log_raw + size_t(w) * (VP_WORDS + VP_MIRROR) * 32u);
+    // unit u of the window = the VP_UNIT bytes at base + VP_UNIT * u; positions are counted from `base` (lane coordinate)
     const uint8_t* base = nullptr;
     uint32_t origin = 0;                     // lane coordinate of the punctured symbol 0
     if (have) {
         const uintptr_t a = reinterpret_cast<uintptr_t>(J->src);
-        base = reinterpret_cast<const uint8_t*>(a & ~uintptr_t(255));
-        origin = uint32_t(a & 255u);
+        base = reinterpret_cast<const uint8_t*>(a & ~uintptr_t(VP_UNIT - 1u));
+        origin = uint32_t(a & (VP_UNIT - 1u));
     }
     PrepSeg S;
     S.seg_end = 0u; S.start = 0u; S.inb = 0u; S.cntw = 0u; S.K = 0u; S.pref_lo = 0u; S.pref_hi = 0u; S.seg = 0u;
+    uint32_t mask8[8];                       // byte masks of the 8 steps of the current segment's code period
+#pragma unroll
+    for (uint32_t g8 = 0; g8 < 8u; g8++) mask8[g8] = 0u;
+    uint32_t mask_seg = 0xFFFFFFFFu;         // segment mask8 was built for
     bool odd = false;   // a segment that does not start on a code period (only dabgpu_viterbi_decode can build one: 128-bit blocks otherwise)
     if (have) {
         uint32_t seg = 0;
@@ -177,32 +184,31 @@ k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, 
         for (uint32_t k = 0; k + 1u < DABGPU_MAX_SEGMENTS; k++) odd = odd || ((J->seg_step_end[k] & 7u) != 0u && J->seg_step_end[k] < N);
     }
     const bool any_odd = __any_sync(FULL_MASK, odd);
-    uint32_t next_unit = have ? ((origin + S.inb) >> 8) : 0u;   // units below this one are in the window (the last two of them)
+    uint32_t next_unit = have ? ((origin + S.inb) / VP_UNIT) : 0u;   // units below this one are in the window (the last two of them)
     uint32_t* __restrict__ dst = sym + size_t(row0) * 32u + lane;
 
 #pragma unroll 1
     for (uint32_t t0 = 0; t0 < padded; t0 += VP_TILE) {
-        // ---- A. refill: the tile reads at most 4 * VP_TILE = 256 symbols from the position of its first step ----
+        // ---- A. refill: the tile reads at most 4 * VP_TILE = 128 symbols from the position of its first step ----
         uint32_t need_unit = 0;
         if (t0 < N) {
             while (t0 >= S.seg_end && S.seg < DABGPU_MAX_SEGMENTS - 1u) prep_seg_load(S, J, S.seg + 1u);
-            need_unit = ((origin + prep_in_index(S, t0) + 4u * VP_TILE - 1u) >> 8) + 1u;
+            need_unit = (origin + prep_in_index(S, t0) + 4u * VP_TILE - 1u) / VP_UNIT + 1u;
         }
         while (__any_sync(FULL_MASK, next_unit < need_unit)) {
             if (next_unit < need_unit) {
-                const uint32_t u = next_unit++, h = (u & 1u) * 64u;
-                {
+                const uint32_t u = next_unit++, h = (u & 1u) * (VP_UNIT / 4u);
+                uint4 P[VP_UNIT / 16u];
 #pragma unroll
-                    for (uint32_t half = 0; half < 2u; half++) {
-                        uint4 P[8];
+                for (uint32_t j = 0; j < VP_UNIT / 16u; j++) P[j] = __ldg(reinterpret_cast<const uint4*>(base + (size_t(u) * VP_UNIT + 16u * j)));
 #pragma unroll
-                        for (uint32_t j = 0; j < 8u; j++) P[j] = __ldg(reinterpret_cast<const uint4*>(base + (size_t(u) * 256u + 128u * half + 16u * j)));
+                for (uint32_t j = 0; j < VP_UNIT / 16u; j++) {
+                    const uint32_t wbase = h + 4u * j;
+                    L[wbase + 0u][lane] = P[j].x; L[wbase + 1u][lane] = P[j].y; L[wbase + 2u][lane] = P[j].z; L[wbase + 3u][lane] = P[j].w;
+                }
+                if (h == 0u) {
 #pragma unroll
-                        for (uint32_t j = 0; j < 8u; j++) {
-                            const uint32_t wbase = h + 32u * half + 4u * j;
-                            L[wbase + 0u][lane] = P[j].x; L[wbase + 1u][lane] = P[j].y; L[wbase + 2u][lane] = P[j].z; L[wbase + 3u][lane] = P[j].w;
-                        }
-                    }
+                    for (uint32_t k = 0; k < VP_MIRROR; k++) L[VP_WORDS + k][lane] = L[k][lane];
                 }
             }
         }
@@ -229,20 +235,36 @@ k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, 
         for (uint32_t p8 = 0; p8 < VP_TILE; p8 += 8u) {
             const uint32_t tp = t0 + p8;
             if (tp >= padded) break;                       // warp-uniform
-            uint32_t lam = 0, cw = 0, plo = 0, phi = 0;
-            if (tp < N) {
-                while (tp >= S.seg_end && S.seg < DABGPU_MAX_SEGMENTS - 1u) prep_seg_load(S, J, S.seg + 1u);
-                lam = origin + S.inb + ((tp - S.start) >> 3) * S.K;
-                const uint32_t nv = min(N - tp, 8u);       // steps of the period that exist: the others get count 0
-                cw = S.cntw & __funnelshift_rc(0xFFFFFFFFu, 0u, 32u - 4u * nv);
-                plo = S.pref_lo; phi = S.pref_hi;
-            }
             uint32_t words[8];
+            if (tp + 8u <= N) {
+                while (tp >= S.seg_end && S.seg < DABGPU_MAX_SEGMENTS - 1u) prep_seg_load(S, J, S.seg + 1u);
+                if (mask_seg != S.seg) {                   // new code: the byte masks of its period (kept-symbol counts per step)
+                    mask_seg = S.seg;
 #pragma unroll
-            for (uint32_t g8 = 0; g8 < 8u; g8++) {
-                const uint32_t cnt = (cw >> (4u * g8)) & 0xFu;
-                const uint32_t pre = ((g8 & 4u) ? (phi >> (8u * (g8 & 3u))) : (plo >> (8u * g8))) & 0xFFu;
-                words[g8] = prep_word(L, lane, lam + pre, cnt);
+                    for (uint32_t g8 = 0; g8 < 8u; g8++) mask8[g8] = prep_mask((S.cntw >> (4u * g8)) & 0xFu);
+                }
+                const uint32_t lam = origin + S.inb + ((tp - S.start) >> 3) * S.K;
+                const uint32_t* __restrict__ row = &L[(lam >> 2) & (VP_WORDS - 1u)][lane];
+                const uint32_t b0 = lam & 3u;
+#pragma unroll
+                for (uint32_t g8 = 0; g8 < 8u; g8++) {
+                    const uint32_t pre = (g8 & 4u) ? __byte_perm(S.pref_hi, 0u, 0x4440u + (g8 & 3u)) : __byte_perm(S.pref_lo, 0u, 0x4440u + g8);
+                    const uint32_t b = b0 + pre;           // byte offset from `row`, < 36: inside the ring or its mirror
+                    const uint32_t* __restrict__ q = row + (b >> 2) * 32u;
+                    words[g8] = __funnelshift_r(q[0], q[32], b * 8u) & mask8[g8];
+                }
+            } else {
+                // the last period of the trellis (tail bits) or beyond it: step by step, zero after the end
+#pragma unroll
+                for (uint32_t g8 = 0; g8 < 8u; g8++) {
+                    const uint32_t t = tp + g8;
+                    uint32_t word = 0;
+                    if (t < N) {
+                        while (t >= S.seg_end && S.seg < DABGPU_MAX_SEGMENTS - 1u) prep_seg_load(S, J, S.seg + 1u);
+                        word = prep_word(L, lane, origin + prep_in_index(S, t), (S.cntw >> (4u * ((t - S.start) & 7u))) & 0xFu);
+                    }
+                    words[g8] = word;
+                }
             }
 #pragma unroll
             for (uint32_t g8 = 0; g8 < 8u; g8++)
