@@ -369,6 +369,17 @@ DABGPU_API int dabgpu_dabplus_process(dabgpu_ctx* ctx, dabgpu_dabplus* p, const 
 DABGPU_API int dabgpu_rs_decode(dabgpu_ctx* ctx, uint8_t* codewords_host, int n_codewords, int nroots, int pad,
                                 int* counts_host, int* positions_host);
 
+/* Packet-mode FEC (ETSI EN 300 401 5.3.5), the Reed-Solomon step of
+ * MSC_Reed_Solomon_Data_Packet_Processor::PerformReedSolomonCorrection (dab/msc/msc_reed_solomon_data_packet_processor.cpp:200-240):
+ * n_frames FEC frames of DABGPU_PACKET_FEC_FRAME_BYTES each = the 2256-byte application data table (the data packets in
+ * transport order) followed by the 192-byte RS data table (data fields of the nine FEC packets, headers and the six
+ * padding bytes removed).  The 12 rows of every frame are decoded as RS(204,188) (16 roots, shortened by 51) and the
+ * application data table is corrected in place; the RS data table is left as received, like the reference.
+ * row_counts (optional) = 12 ints per frame, the return value of Reed_Solomon_Decoder::Decode per row (-1 = uncorrectable). */
+#define DABGPU_PACKET_FEC_FRAME_BYTES 2448
+#define DABGPU_PACKET_FEC_ROWS 12
+DABGPU_API int dabgpu_packet_fec_decode(dabgpu_ctx* ctx, uint8_t* frames_host, int n_frames, int* row_counts_host);
+
 /* Whole-chain convenience for throughput runs: OFDM advance + channel decode of the frames produced. */
 typedef struct {
     uint64_t frames_demodulated;   /* totals since context creation */

@@ -112,6 +112,11 @@ class RefLib:
             L.ref_iq_convert.restype = C.c_long
             L.ref_softbits_to_bytes.argtypes = [_i8p, C.c_size_t, _u8p]
             L.ref_bytes_to_softbits.argtypes = [_u8p, C.c_size_t, _i8p]
+        if hasattr(L, "ref_pktfec_create"):
+            L.ref_pktfec_create.restype = C.c_void_p
+            L.ref_pktfec_destroy.argtypes = [C.c_void_p]
+            L.ref_pktfec_read_packet.argtypes = [C.c_void_p, _u8p, C.c_int, _u8p, C.c_int, C.POINTER(C.c_int)]
+            L.ref_pktfec_read_packet.restype = C.c_long
         if hasattr(L, "ref_fig_create"):
             L.ref_fig_create.restype = C.c_void_p
             L.ref_fig_destroy.argtypes = [C.c_void_p]
@@ -266,6 +271,40 @@ class RefAac:
         n = self.lib.ref_aac_process(self.h, frame, frame.size, self.log, self.log.size)
         assert n <= self.log.size
         return parse_event_log(self.log[:n].tobytes())
+
+
+def parse_packet_log(buf: bytes) -> List[Tuple[bytes, bool]]:
+    """flat callback log of the packet-mode FEC processors -> [(packet bytes, is_corrected)]"""
+    out, off = [], 0
+    while off + 8 <= len(buf):
+        n, corrected = np.frombuffer(buf, dtype="<i4", count=2, offset=off)
+        off += 8
+        out.append((bytes(buf[off:off + int(n)]), bool(corrected)))
+        off += (int(n) + 3) & ~3
+    return out
+
+
+class RefPacketFec:
+    """MSC_Reed_Solomon_Data_Packet_Processor of the reference build (msc_reed_solomon_data_packet_processor.cpp)."""
+
+    def __init__(self):
+        self.lib = RefLib.get().L
+        self.h = self.lib.ref_pktfec_create()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_pktfec_destroy(self.h)
+            self.h = None
+
+    def read_packet(self, buf: np.ndarray) -> Tuple[int, List[Tuple[bytes, bool]]]:
+        b = np.ascontiguousarray(buf, dtype=np.uint8)
+        if b.size == 0:
+            b = np.zeros(1, dtype=np.uint8)[:0].copy()
+        log = np.zeros(1 << 16, dtype=np.uint8)
+        n = C.c_int(0)
+        used = self.lib.ref_pktfec_read_packet(self.h, b if b.size else np.zeros(1, dtype=np.uint8), int(buf.size), log, log.size, C.byref(n))
+        assert used >= 0
+        return int(used), parse_packet_log(log[:n.value].tobytes())
 
 
 def ref_iq_convert(mode: str, raw: np.ndarray) -> np.ndarray:
@@ -527,6 +566,104 @@ class PortRS:
         pos = np.zeros(32, dtype=np.int32)
         cnt = self.lib.dabo_rs_decode(self.nroots, self.pad, d, pos)
         return cnt, d, pos[:max(cnt, 0)].copy()
+
+
+class PortPacketFec:
+    """Restatement of MSC_Reed_Solomon_Data_Packet_Processor (msc_reed_solomon_data_packet_processor.cpp:49-258) on top of the
+    C restatement's RS decoder: a 2472-byte ring of whole packets, nine FEC packets with counters 0..8 close a set, the 12 rows
+    of the 204-column table are decoded as RS(204,188) and only the application data table is corrected."""
+    LENGTHS = (24, 48, 72, 96)
+    RING = 2256 + 9 * 24
+
+    def __init__(self):
+        self.rs = PortRS(16, 51)
+        self.ring = np.zeros(self.RING, dtype=np.uint8)
+        self.rd = self.wr = self.fill = 0
+        self.last = None
+
+    def _pop(self):
+        if self.fill == 0:
+            return None
+        n = self.LENGTHS[int(self.ring[self.rd]) >> 6]
+        pkt = bytes(self.ring[(self.rd + np.arange(n)) % self.RING])
+        self.fill -= n
+        self.rd = (self.rd + n) % self.RING
+        return pkt
+
+    def _push(self, pkt: np.ndarray, lid: int):
+        n = self.LENGTHS[lid]
+        while self.RING - self.fill < n:                       # msc_reed_solomon_data_packet_processor.cpp:137-148
+            m = self.LENGTHS[int(self.ring[self.rd]) >> 6]
+            self.fill -= m
+            self.rd = (self.rd + m) % self.RING
+        idx = (self.wr + np.arange(n)) % self.RING
+        self.ring[idx] = pkt[:n]
+        self.ring[self.wr] = (int(pkt[0]) & 0x3F) | (lid << 6)    # :151-153 the length id is the one the processor decided on
+        self.fill += n
+        self.wr = (self.wr + n) % self.RING
+
+    def _clear(self, out):
+        while True:
+            p = self._pop()
+            if p is None:
+                break
+            out.append((p, False))
+
+    def _correct(self, out):
+        at = lambda off: (self.rd + off) % self.RING
+        table = np.zeros(192, dtype=np.uint8)
+        for i in range(9):                                     # :203-219
+            n = 22 if i < 8 else 16
+            table[22 * i:22 * i + n] = self.ring[[at(2256 + 24 * i + 2 + j) for j in range(n)]]
+        for y in range(12):                                    # :222-258
+            cw = np.concatenate([self.ring[[at(12 * x + y) for x in range(188)]], table[[12 * i + y for i in range(16)]]])
+            cnt, fixed, pos = self.rs.decode(cw)
+            if cnt < 0:
+                continue
+            for p in pos[:cnt]:
+                x = int(p) - 51
+                if 0 <= x < 188:
+                    self.ring[at(12 * x + y)] = fixed[x]
+        total = 0
+        while total < 2256:
+            p = self._pop()
+            if p is None:
+                break
+            out.append((p, True))
+            total += len(p)
+
+    def read_packet(self, buf: np.ndarray) -> Tuple[int, List[Tuple[bytes, bool]]]:
+        buf = np.asarray(buf, dtype=np.uint8)
+        out: List[Tuple[bytes, bool]] = []
+        if buf.size < 2:
+            return int(buf.size), out
+        lid = int(buf[0]) >> 6
+        counter = (int(buf[0]) >> 2) & 0xF
+        address = ((int(buf[0]) & 3) << 8) | int(buf[1])
+        is_fec = address == 0x3FE
+        if is_fec:
+            lid = 0
+        n = self.LENGTHS[lid]
+        if buf.size < n:
+            return int(buf.size), out
+        self._push(buf, lid)
+        if not is_fec:
+            return n, out
+        invalid = (counter != self.last + 1) if self.last is not None else (counter != 0)
+        if invalid:
+            self.last = None
+            self._clear(out)
+            return n, out
+        self.last = counter
+        if counter != 8:
+            return n, out
+        if self.fill != self.RING:
+            self._clear(out)
+        else:
+            self._correct(out)
+        self.last = None
+        self.rd = self.wr = self.fill = 0
+        return n, out
 
 
 class PortAac:

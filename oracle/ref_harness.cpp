@@ -62,6 +62,7 @@
 #include "dab/fic/fic_decoder.h"
 #include "dab/msc/cif_deinterleaver.h"
 #include "dab/msc/msc_decoder.h"
+#include "dab/msc/msc_reed_solomon_data_packet_processor.h"
 #include "viterbi_config.h"
 
 #define API extern "C" __attribute__((visibility("default")))
@@ -219,6 +220,37 @@ API void* ref_rs_create(int symsize, int gfpoly, int fcr, int prim, int nroots, 
 API void ref_rs_destroy(void* h) { delete (RefRs*)h; }
 API int ref_rs_decode(void* h, uint8_t* data, int* eras_pos, int no_eras) {
     return ((RefRs*)h)->d->Decode(data, eras_pos, no_eras);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Packet-mode FEC (MSC_Reed_Solomon_Data_Packet_Processor): callbacks serialised into a flat log
+// record: int32 nbytes, int32 is_corrected, then the packet (padded to 4)
+// ---------------------------------------------------------------------------------------------
+struct RefPktFec {
+    MSC_Reed_Solomon_Data_Packet_Processor proc;
+    std::vector<uint8_t> log;
+};
+API void* ref_pktfec_create() {
+    auto* r = new RefPktFec();
+    r->proc.SetCallback([r](tcb::span<const uint8_t> pkt, bool corrected) {
+        const int32_t hdr[2] = {int32_t(pkt.size()), corrected ? 1 : 0};
+        const size_t off = r->log.size(), pad = (pkt.size() + 3u) & ~size_t(3);
+        r->log.resize(off + sizeof(hdr) + pad, 0);
+        memcpy(&r->log[off], hdr, sizeof(hdr));
+        if (!pkt.empty()) memcpy(&r->log[off + sizeof(hdr)], pkt.data(), pkt.size());
+    });
+    return r;
+}
+API void ref_pktfec_destroy(void* h) { delete (RefPktFec*)h; }
+// returns the number of bytes ReadPacket consumed; the callbacks fired by this call are appended to log_out
+API long ref_pktfec_read_packet(void* h, const uint8_t* buf, int n, uint8_t* log_out, int log_cap, int* log_bytes) {
+    auto* r = (RefPktFec*)h;
+    r->log.clear();
+    const size_t used = r->proc.ReadPacket({buf, size_t(n)});
+    *log_bytes = int(r->log.size());
+    if (int(r->log.size()) > log_cap) return -1;
+    if (!r->log.empty()) memcpy(log_out, r->log.data(), r->log.size());
+    return long(used);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -11,7 +11,7 @@ template <int V>
 __global__ void __launch_bounds__(512, 1) k(const uint32_t* __restrict__ sym, uint2* __restrict__ dec, unsigned long long* out, long long* cyc, const VlConst kc) {
     VlState S;
     vl_reset(S);
-    uint64_t fe = 0;
+    uint64_t fe = 0; uint32_t frel = 0;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t* s = sym + (threadIdx.x & 31);
     uint2* d = dec + size_t(tid);
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(512, 1) k(const uint32_t* __restrict__ sym, ui
         uint32_t w[5], dd[10];
 #pragma unroll
         for (int q = 0; q < 5; q++) w[q] = __ldg(s + (g * 5 + q) * 32);
-        if (V == 0) vl_step5(S, w, g * 5, GROUPS * 5, dd, fe, kc);
+        if (V == 0) vl_step5(S, w, g * 5, GROUPS * 5, dd, frel, kc);
         else {
             uint32_t Ea[8], Eia[8], Eb[8], Eib[8];
             vl_branch<0>(w[0], Ea, Eia, kc);
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(512, 1) k(const uint32_t* __restrict__ sym, ui
     uint32_t x = 0;
 #pragma unroll
     for (int i = 0; i < 32; i++) x ^= S.R[i];
-    out[tid] = fe + x;
+    out[tid] = fe + x + vl_final_error(S, frel);
     if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
 template <int V> void run(const char* name, const uint32_t* sym, uint2* dec, unsigned long long* out, long long* cyc) {

@@ -104,6 +104,7 @@ EXPORTS = [
     "dabgpu_autocfg_create", "dabgpu_autocfg_destroy", "dabgpu_autocfg_push_fibs", "dabgpu_autocfg_dump", "dabgpu_autocfg_runnable",
     "dabgpu_host_alloc", "dabgpu_host_free", "dabgpu_ofdm_get_frame_data_vec", "dabgpu_ofdm_get_correlation_buffer", "dabgpu_autocfg_applied", "dabgpu_msc_add_subchannel", "dabgpu_msc_remove_subchannel", "dabgpu_chan_join",
     "dabgpu_autocfg_apply", "dabgpu_ofdm_get_response", "dabgpu_ofdm_get_frame_fft", "dabgpu_iq_convert", "dabgpu_softbits_to_bytes", "dabgpu_bytes_to_softbits",
+    "dabgpu_packet_fec_decode",
 ]
 
 _lib = None
@@ -154,6 +155,7 @@ def load_library() -> C.CDLL:
     L.dabgpu_chan_get_msc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int)]
     L.dabgpu_chan_get_dabplus_events.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.dabgpu_rs_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.dabgpu_packet_fec_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.dabgpu_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     L.dabgpu_ofdm_set_config.argtypes = [C.c_void_p, C.POINTER(OfdmConfig)]
     L.dabgpu_fic_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -378,6 +380,14 @@ class DabGpu:
         pos = np.zeros((cw.shape[0], nroots), dtype=np.int32)
         _check(self.L.dabgpu_rs_decode(self.h, _ptr(cw), cw.shape[0], nroots, pad, _ptr(counts), _ptr(pos)))
         return counts, cw, pos
+
+    def packet_fec_decode(self, frames: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """frames [n][2448] (application data table + RS data table, transport order) -> (corrected frames, row counts [n][12])"""
+        fr = np.ascontiguousarray(frames, dtype=np.uint8).copy()
+        assert fr.ndim == 2 and fr.shape[1] == 2448
+        counts = np.zeros((fr.shape[0], 12), dtype=np.int32)
+        _check(self.L.dabgpu_packet_fec_decode(self.h, _ptr(fr), fr.shape[0], _ptr(counts)))
+        return fr, counts
 
     def fic_decode(self, soft: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         """soft: [n_groups, 2304] int8 -> (fibs [n_groups, 3, 32], crc_ok [n_groups, 3])"""

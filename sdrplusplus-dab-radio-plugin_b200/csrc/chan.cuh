@@ -70,16 +70,16 @@ __device__ __forceinline__ ChanPick chan_pick_frame(const ChanDev& C, const uint
 __global__ void k_chan_build_jobs(const ChanDev C, VitJobDev* __restrict__ jobs, const int first_stream, const int n_streams, VlPlan* __restrict__ count_plan) {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = uint32_t(n_streams) * C.jobs_per_stream;
-    if (gid >= total) return;
-    const uint32_t si = gid / C.jobs_per_stream, j = gid - si * C.jobs_per_stream;
+    const bool in_range = gid < total;            // no early return: the histogram below is taken by whole warps
+    const uint32_t si = in_range ? gid / C.jobs_per_stream : 0u, j = in_range ? gid - si * C.jobs_per_stream : 0u;
     const uint32_t s = uint32_t(first_stream) + si;
     VitJobDev J;
     memset(&J, 0, sizeof(J));
     const ChanPick pick = chan_pick_frame(C, s);
     const uint32_t t = pick.t;
-    const bool has_frame = pick.has_frame;
+    const bool has_frame = pick.has_frame && in_range;
     const uint32_t nb_cifs = C.geom.nb_cifs;
-    if (j == 0) {
+    if (j == 0 && in_range) {
         C.status[2 * s + 0] = has_frame ? 1 : 0;
         C.status[2 * s + 1] = int32_t(t);
     }
@@ -122,11 +122,8 @@ __global__ void k_chan_build_jobs(const ChanDev C, VitJobDev* __restrict__ jobs,
             }
         }
     }
-    jobs[gid] = J;
-    if (count_plan != nullptr && J.total_steps != 0u) {
-        if (J.total_steps >= VL_MAX_STEPS) count_plan->oversize = 1u;
-        else atomicAdd(&count_plan->count[vl_bucket(J.total_steps)], 1u);
-    }
+    if (in_range) jobs[gid] = J;
+    if (count_plan != nullptr) vl_count_warp(count_plan, J.total_steps);
 }
 
 // CIF_Deinterleaver::Deinterleave (dab/msc/cif_deinterleaver.cpp:20-71) for the nb_cifs CIFs of the frame every stream decodes in

@@ -974,6 +974,14 @@ int dabgpu_rs_decode(dabgpu_ctx* ctx, uint8_t* codewords_host, int n_codewords, 
     return dabplus_rs_decode_batch(ctx->dabplus, codewords_host, n_codewords, nroots, pad, counts_host, positions_host, ctx->stream, &ctx->launches);
 }
 
+int dabgpu_packet_fec_decode(dabgpu_ctx* ctx, uint8_t* frames_host, int n_frames, int* row_counts_host) {
+    if (!ctx || !frames_host) return set_error(DABGPU_ERR_INVALID, "null argument");
+    if (n_frames < 0) return set_error(DABGPU_ERR_INVALID, "n_frames %d", n_frames);
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(join_dabplus(ctx));
+    return dabplus_packet_fec_batch(ctx->dabplus, frames_host, n_frames, row_counts_host, ctx->stream, &ctx->launches);
+}
+
 int dabgpu_fic_decode(dabgpu_ctx* ctx, const int8_t* soft_host, int n_groups, uint8_t* fibs_host, uint8_t* crc_ok) {
     if (!ctx || !soft_host || !fibs_host || !crc_ok) return set_error(DABGPU_ERR_INVALID, "null argument");
     if (n_groups <= 0) return DABGPU_OK;

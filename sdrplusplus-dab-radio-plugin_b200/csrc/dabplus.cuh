@@ -404,6 +404,34 @@ __global__ void k_rs_batch(uint8_t* __restrict__ cw, const int n_cw, const int n
     counts[i] = cnt;
 }
 
+// Packet-mode FEC frame (ETSI EN 300 401 5.3.5; MSC_Reed_Solomon_Data_Packet_Processor::PerformReedSolomonCorrection,
+// msc_reed_solomon_data_packet_processor.cpp:200-240): a frame is the 2256-byte application data table followed by the
+// 192-byte RS data table, both in transport order.  Because 188 * 12 = 2256 the two tables form ONE column-major 204 x 12
+// matrix: byte x of row y sits at x * 12 + y, so the row codewords are stride-12 reads and nothing has to be transposed.
+// One thread per (frame, row); a correction is written back only into the application data table (x < 188), like the
+// reference, which leaves the FEC packets alone.
+#define PKT_FEC_ROWS 12
+#define PKT_FEC_DATA 188
+#define PKT_FEC_FRAME_BYTES 2448   // 204 * 12
+__global__ void k_packet_fec(uint8_t* __restrict__ frames, const int n_frames, int* __restrict__ counts) {
+    __shared__ DpShared sh;
+    dp_load_shared(sh);
+    const GfTables T{sh.gf_ex, sh.gf_lg};
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_frames * PKT_FEC_ROWS) return;
+    const int f = i / PKT_FEC_ROWS, y = i - f * PKT_FEC_ROWS;
+    uint8_t* row = frames + size_t(f) * PKT_FEC_FRAME_BYTES + y;
+    constexpr int nroots = 16, pad = 51, n = 204;
+    uint8_t S[RS_MAX_ROOTS], loc[RS_MAX_ROOTS], xv[RS_MAX_ROOTS], ap[RS_MAX_ROOTS];
+    int cnt = 0;
+    if (rs_syndromes(T, row, PKT_FEC_ROWS, n, nroots, S)) cnt = rs_solve(T, S, nroots, pad, loc, xv, ap);
+    for (int j = 0; j < cnt; j++) {
+        const int x = int(loc[j]) - pad;
+        if (ap[j] && x < PKT_FEC_DATA) row[size_t(x) * PKT_FEC_ROWS] ^= xv[j];
+    }
+    counts[i] = cnt;
+}
+
 static int dabplus_init(DabPlusState& S, int max_streams, int max_subs, int nb_cifs) {
     S.max_streams = max_streams; S.max_subs = max_subs; S.nb_cifs = nb_cifs;
     int rc;
@@ -500,6 +528,22 @@ static int dabplus_rs_decode_batch(DabPlusState& S, uint8_t* cw_host, int n_cw, 
     CUDA_TRY(cudaMemcpyAsync(cw_host, S.d_rs_cw.p, size_t(n_cw) * n, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaMemcpyAsync(counts_host, S.d_rs_cnt.p, size_t(n_cw) * 4, cudaMemcpyDeviceToHost, stream));
     if (pos_host) CUDA_TRY(cudaMemcpyAsync(pos_host, S.d_rs_pos.p, size_t(n_cw) * nroots * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return DABGPU_OK;
+}
+
+static int dabplus_packet_fec_batch(DabPlusState& S, uint8_t* frames_host, int n_frames, int* counts_host, cudaStream_t stream, uint64_t* launches) {
+    if (n_frames <= 0) return DABGPU_OK;
+    int rc;
+    const size_t bytes = size_t(n_frames) * PKT_FEC_FRAME_BYTES, n_rows = size_t(n_frames) * PKT_FEC_ROWS;
+    if ((rc = S.d_rs_cw.alloc(bytes))) return rc;
+    if ((rc = S.d_rs_cnt.alloc(n_rows * 4))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(S.d_rs_cw.p, frames_host, bytes, cudaMemcpyHostToDevice, stream));
+    k_packet_fec<<<unsigned((n_rows + 63) / 64), 64, 0, stream>>>(S.d_rs_cw.as<uint8_t>(), n_frames, S.d_rs_cnt.as<int>());
+    (*launches)++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(frames_host, S.d_rs_cw.p, bytes, cudaMemcpyDeviceToHost, stream));
+    if (counts_host) CUDA_TRY(cudaMemcpyAsync(counts_host, S.d_rs_cnt.p, n_rows * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     return DABGPU_OK;
 }

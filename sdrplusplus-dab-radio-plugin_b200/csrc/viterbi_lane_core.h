@@ -209,7 +209,9 @@ VL_HD uint32_t vl_min_all(const uint32_t (&R)[32]) {
 
 // Bookkeeping after the step with index t (0-based): the reference's renormalisation test and the capture of the path
 // error of a trellis that ends at step n_steps - 1.  State 0 is the low half of register 0 in every layout.
-VL_HD void vl_after_step(VlState& S, const uint32_t t, const uint32_t n_steps, uint64_t& final_err) {
+// final_rel = metric of state 0 after the last step, in the reference's domain; the renormalisations stop with the trellis, so
+// the path error chainback returns is S.acc_err + final_rel once the loop is over (vl_final_error).
+VL_HD void vl_after_step(VlState& S, const uint32_t t, const uint32_t n_steps, uint32_t& final_rel) {
     const int32_t r0 = int32_t(S.R[0] & 0xFFFFu);
     if (r0 >= S.thr && t < n_steps) {
         // ViterbiDecoder_AVX_u16::renormalise (viterbi_decoder_avx_u16.h:138-170): subtract the minimum over the 64 states
@@ -217,19 +219,22 @@ VL_HD void vl_after_step(VlState& S, const uint32_t t, const uint32_t n_steps, u
         S.acc_err += uint64_t(uint32_t(mn));
         vl_set_off(S, S.off - mn);
     }
-    if (t + 1u == n_steps) final_err = S.acc_err + uint64_t(uint32_t(r0 + S.off));
+    if (t + 1u == n_steps) final_rel = uint32_t(r0 + S.off);
 }
+VL_HD uint64_t vl_final_error(const VlState& S, const uint32_t final_rel) { return S.acc_err + uint64_t(final_rel); }
 
-// Five trellis steps t0 .. t0+4 starting and ending in layout 0.  dec[2k], dec[2k+1] = decision words of step t0+k.
-VL_HD void vl_step5(VlState& S, const uint32_t (&w)[VL_UNROLL], const uint32_t t0, const uint32_t n_steps, uint32_t (&dec)[2 * VL_UNROLL],
-                    uint64_t& final_err, const VlConst kc) {
-    uint32_t Ea[8], Eia[8], Eb[8], Eib[8];
+// Five trellis steps t0 .. t0+4 starting and ending in layout 0.  emit(k, d0, d1) receives the decision words of step t0+k as
+// soon as they exist (the kernel stores them at once: ten live registers less than keeping them to the end of the iteration).
+template <class Emit>
+VL_HD void vl_step5_emit(VlState& S, const uint32_t (&w)[VL_UNROLL], const uint32_t t0, const uint32_t n_steps, Emit&& emit, uint32_t& final_rel,
+                         const VlConst kc) {
+    uint32_t Ea[8], Eia[8], Eb[8], Eib[8], d0, d1;
     vl_branch<0>(w[0], Ea, Eia, kc);
-    vl_acs<0>(S.R, Ea, Eia, S.CL, dec[0], dec[1], kc); vl_branch<1>(w[1], Eb, Eib, kc); vl_after_step(S, t0 + 0u, n_steps, final_err);
-    vl_acs<1>(S.R, Eb, Eib, S.CL, dec[2], dec[3], kc); vl_branch<2>(w[2], Ea, Eia, kc); vl_after_step(S, t0 + 1u, n_steps, final_err);
-    vl_acs<2>(S.R, Ea, Eia, S.CL, dec[4], dec[5], kc); vl_branch<3>(w[3], Eb, Eib, kc); vl_after_step(S, t0 + 2u, n_steps, final_err);
-    vl_acs<3>(S.R, Eb, Eib, S.CL, dec[6], dec[7], kc); vl_branch<4>(w[4], Ea, Eia, kc); vl_after_step(S, t0 + 3u, n_steps, final_err);
-    vl_acs<4>(S.R, Ea, Eia, S.CL, dec[8], dec[9], kc); vl_after_step(S, t0 + 4u, n_steps, final_err);
+    vl_acs<0>(S.R, Ea, Eia, S.CL, d0, d1, kc); emit(0, d0, d1); vl_branch<1>(w[1], Eb, Eib, kc); vl_after_step(S, t0 + 0u, n_steps, final_rel);
+    vl_acs<1>(S.R, Eb, Eib, S.CL, d0, d1, kc); emit(1, d0, d1); vl_branch<2>(w[2], Ea, Eia, kc); vl_after_step(S, t0 + 1u, n_steps, final_rel);
+    vl_acs<2>(S.R, Ea, Eia, S.CL, d0, d1, kc); emit(2, d0, d1); vl_branch<3>(w[3], Eb, Eib, kc); vl_after_step(S, t0 + 2u, n_steps, final_rel);
+    vl_acs<3>(S.R, Eb, Eib, S.CL, d0, d1, kc); emit(3, d0, d1); vl_branch<4>(w[4], Ea, Eia, kc); vl_after_step(S, t0 + 3u, n_steps, final_rel);
+    vl_acs<4>(S.R, Ea, Eia, S.CL, d0, d1, kc); emit(4, d0, d1); vl_after_step(S, t0 + 4u, n_steps, final_rel);
     vl_repack(S.R);
     // own renormalisation: bring rel[0] back to VL_ORIGIN (delta >= 0: metrics never decrease)
     const uint32_t delta = (S.R[0] & 0xFFFFu) - VL_ORIGIN;
@@ -237,6 +242,12 @@ VL_HD void vl_step5(VlState& S, const uint32_t (&w)[VL_UNROLL], const uint32_t t
 #pragma unroll
     for (int i = 0; i < 32; i++) S.R[i] -= d2;
     vl_set_off(S, S.off + int32_t(delta));
+}
+
+// the same with the decision words returned: dec[2k], dec[2k+1] = step t0+k
+VL_HD void vl_step5(VlState& S, const uint32_t (&w)[VL_UNROLL], const uint32_t t0, const uint32_t n_steps, uint32_t (&dec)[2 * VL_UNROLL],
+                    uint32_t& final_rel, const VlConst kc) {
+    vl_step5_emit(S, w, t0, n_steps, [&](const int k, const uint32_t d0, const uint32_t d1) { dec[2 * k] = d0; dec[2 * k + 1] = d1; }, final_rel, kc);
 }
 
 // Traceback: the decision bit of new state n at a step whose index is k modulo 5.

@@ -37,13 +37,20 @@ struct VlPlan {
     uint32_t row_base[VL_BUCKETS];    // first symbol row of the class
 };
 
+// Histogram entry of one trellis per lane (0 steps = none), called by whole warps: the lanes of a class elect a leader that adds
+// their number with one atomic.  A call carries two or three classes, one atomic per trellis serialised 78 000 of them on two
+// addresses (55 us per 1024-stream step).
+__device__ __forceinline__ void vl_count_warp(VlPlan* __restrict__ plan, const uint32_t steps) {
+    uint32_t b = 0xFFFFFFFFu;
+    if (steps >= VL_MAX_STEPS) plan->oversize = 1u;
+    else if (steps != 0u) b = vl_bucket(steps);
+    const uint32_t peers = __match_any_sync(FULL_MASK, b);
+    if (b != 0xFFFFFFFFu && (threadIdx.x & 31u) == uint32_t(__ffs(int(peers)) - 1)) atomicAdd(&plan->count[b], uint32_t(__popc(peers)));
+}
+
 __global__ void k_vit_count(const VitJobDev* __restrict__ jobs, const int n_jobs, VlPlan* __restrict__ plan) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= n_jobs) return;
-    const uint32_t steps = jobs[gid].total_steps;
-    if (steps == 0u) return;
-    if (steps >= VL_MAX_STEPS) { plan->oversize = 1u; return; }
-    atomicAdd(&plan->count[vl_bucket(steps)], 1u);
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;    // blockDim is a multiple of 32: whole warps reach vl_count_warp
+    vl_count_warp(plan, gid < n_jobs ? jobs[gid].total_steps : 0u);
 }
 
 // mode: 0 = lanes when at least min_jobs trellises are active, 1 = always, 2 = never
@@ -72,11 +79,17 @@ __global__ void k_vit_plan(VlPlan* __restrict__ plan, const int mode, const uint
 
 __global__ void k_vit_scatter(const VitJobDev* __restrict__ jobs, const int n_jobs, VlPlan* __restrict__ plan, uint32_t* __restrict__ list) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= n_jobs || !plan->use_lanes) return;
-    const uint32_t steps = jobs[gid].total_steps;
-    if (steps == 0u) return;
-    const uint32_t b = vl_bucket(steps);
-    list[plan->list_base[b] + atomicAdd(&plan->cursor[b], 1u)] = uint32_t(gid);
+    if (!plan->use_lanes) return;
+    const uint32_t steps = gid < n_jobs ? jobs[gid].total_steps : 0u;
+    const uint32_t b = steps != 0u ? vl_bucket(steps) : 0xFFFFFFFFu;
+    // one cursor atomic per class and warp (see vl_count_warp); the lanes of the class take consecutive entries
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t peers = __match_any_sync(FULL_MASK, b);
+    const uint32_t leader = uint32_t(__ffs(int(peers)) - 1);
+    uint32_t base = 0;
+    if (b != 0xFFFFFFFFu && lane == leader) base = atomicAdd(&plan->cursor[b], uint32_t(__popc(peers)));
+    base = __shfl_sync(FULL_MASK, base, int(leader));
+    if (b != 0xFFFFFFFFu) list[plan->list_base[b] + base + uint32_t(__popc(peers & ((1u << lane) - 1u)))] = uint32_t(gid);
 }
 
 // group index -> class, first list entry, number of trellises, first symbol row.  Called by whole warps: every lane tests two
@@ -374,7 +387,7 @@ k_viterbi_lanes(const VitJobDev* __restrict__ jobs, VlPlan* __restrict__ plan, c
         {
             VlState S;
             vl_reset(S);
-            uint64_t final_err = 0;
+            uint32_t final_rel = 0;
             uint32_t w[VL_UNROLL];
 #pragma unroll
             for (int k = 0; k < VL_UNROLL; k++) w[k] = __ldg(srow + size_t(k) * 32u);
@@ -383,15 +396,12 @@ k_viterbi_lanes(const VitJobDev* __restrict__ jobs, VlPlan* __restrict__ plan, c
                 uint32_t wn[VL_UNROLL];
 #pragma unroll
                 for (int k = 0; k < VL_UNROLL; k++) wn[k] = __ldg(srow + size_t(t0 + VL_UNROLL + k) * 32u);
-                uint32_t d[2 * VL_UNROLL];
-                vl_step5(S, w, t0, N, d, final_err, kc);
+                uint2* __restrict__ drow = dec + size_t(t0) * 32u;
+                vl_step5_emit(S, w, t0, N, [&](const int k, const uint32_t d0, const uint32_t d1) { drow[k * 32] = make_uint2(d0, d1); }, final_rel, kc);
 #pragma unroll
-                for (int k = 0; k < VL_UNROLL; k++) {
-                    dec[size_t(t0 + k) * 32u] = make_uint2(d[2 * k], d[2 * k + 1]);
-                    w[k] = wn[k];
-                }
+                for (int k = 0; k < VL_UNROLL; k++) w[k] = wn[k];
             }
-            if (have && J->path_error != nullptr) *J->path_error = final_err;
+            if (have && J->path_error != nullptr) *J->path_error = vl_final_error(S, final_rel);
         }
 
         vl_traceback<TB>(dec, J, have, n_out_bytes, flags, out, prbs_words);

@@ -12,6 +12,7 @@
 //   FIC_Decoder                      vendor/DAB-Radio/src/dab/fic/fic_decoder.h:17-38
 //   MSC_Decoder, Subchannel          vendor/DAB-Radio/src/dab/msc/msc_decoder.h:19-38, dab/database/dab_database_entities.h
 //   Reed_Solomon_Decoder             vendor/DAB-Radio/src/dab/algorithms/reed_solomon_decoder.h:13-27
+//   MSC_Reed_Solomon_Data_Packet_Processor vendor/DAB-Radio/src/dab/msc/msc_reed_solomon_data_packet_processor.h:14-45
 //   AAC_Frame_Processor              vendor/DAB-Radio/src/dab/audio/aac_frame_processor.h:13-82
 //   BasicRadio::Process              vendor/DAB-Radio/src/basic_radio/basic_radio.h:25-56, basic_radio.cpp:41-65
 //   Observable                       vendor/DAB-Radio/src/utility/observable.h
@@ -543,6 +544,102 @@ public:
         if (!m_ctx->check(dabgpu_rs_decode(m_ctx->get(), data, 1, m_nroots, m_pad, &count, pos.data()))) return -1;
         if (eras_pos) for (int i = 0; i < count; i++) eras_pos[i] = pos[size_t(i)];
         return count;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// MSC_Reed_Solomon_Data_Packet_Processor: packet-mode FEC (ETSI EN 300 401 5.3.5).  Packets are queued until the nine FEC
+// packets of a set have arrived; the Reed-Solomon step over the 12 rows of the set runs on the GPU
+// (dabgpu_packet_fec_decode), the packets then leave through the callback flagged "corrected".  Packets that cannot be
+// protected (a broken FEC counter sequence, an incomplete set) leave flagged "not corrected", in arrival order, like the
+// reference (msc_reed_solomon_data_packet_processor.cpp:49-258).
+// ---------------------------------------------------------------------------------------------------------------
+class MSC_Reed_Solomon_Data_Packet_Processor {
+public:
+    using Callback = std::function<void(span<const uint8_t>, bool)>;   // packet, is_corrected
+private:
+    static constexpr size_t kTableBytes = 2256, kFecPackets = 9, kFecPacketBytes = 24, kFecHeader = 2;
+    static constexpr size_t kCapacity = kTableBytes + kFecPackets * kFecPacketBytes;
+    static constexpr uint16_t kFecAddress = 0x3FE;
+    static size_t length_of(uint8_t id) { return 24u * (size_t(id & 3u) + 1u); }   // table 6: 24, 48, 72, 96
+
+    std::shared_ptr<Context> m_ctx;
+    std::vector<uint8_t> m_store = std::vector<uint8_t>(kCapacity);   // circular queue of whole packets
+    size_t m_front = 0, m_back = 0, m_fill = 0;
+    int m_fec_seen = -1;                                              // counter of the last FEC packet of the running set
+    std::vector<uint8_t> m_packet, m_frame = std::vector<uint8_t>(DABGPU_PACKET_FEC_FRAME_BYTES);
+    Callback m_callback;
+
+    uint8_t& cell(size_t offset_from_front) { return m_store[(m_front + offset_from_front) % kCapacity]; }
+    void enqueue(span<const uint8_t> packet, uint8_t length_id) {
+        while (kCapacity - m_fill < packet.size()) {   // the oldest packets make room, unannounced
+            const size_t n = length_of(uint8_t(m_store[m_front] >> 6));
+            m_fill -= n;
+            m_front = (m_front + n) % kCapacity;
+        }
+        for (size_t i = 0; i < packet.size(); i++) m_store[(m_back + i) % kCapacity] = packet[i];
+        m_store[m_back] = uint8_t((packet[0] & 0x3Fu) | (length_id << 6));   // a FEC packet is always stored as 24 bytes
+        m_fill += packet.size();
+        m_back = (m_back + packet.size()) % kCapacity;
+    }
+    bool dequeue() {
+        if (m_fill == 0) return false;
+        const size_t n = length_of(uint8_t(m_store[m_front] >> 6));
+        m_packet.resize(n);
+        for (size_t i = 0; i < n; i++) m_packet[i] = cell(i);
+        m_fill -= n;
+        m_front = (m_front + n) % kCapacity;
+        return true;
+    }
+    void flush_uncorrected() {
+        while (dequeue())
+            if (m_callback) m_callback({m_packet.data(), m_packet.size()}, false);
+    }
+    void correct_and_flush() {
+        // FEC frame for the device: the application data table as queued, then the data fields of the nine FEC packets
+        for (size_t i = 0; i < kTableBytes; i++) m_frame[i] = cell(i);
+        size_t w = kTableBytes;
+        for (size_t k = 0; k < kFecPackets; k++) {
+            const size_t n = (k + 1 < kFecPackets) ? kFecPacketBytes - kFecHeader : kFecPacketBytes - kFecHeader - 6;   // six padding bytes end the set
+            for (size_t j = 0; j < n; j++) m_frame[w++] = cell(kTableBytes + k * kFecPacketBytes + kFecHeader + j);
+        }
+        bool ok;
+        {
+            std::lock_guard<std::mutex> lock(m_ctx->mutex());
+            ok = m_ctx->check(dabgpu_packet_fec_decode(m_ctx->get(), m_frame.data(), 1, nullptr));
+        }
+        if (ok) for (size_t i = 0; i < kTableBytes; i++) cell(i) = m_frame[i];
+        size_t delivered = 0;
+        while (delivered < kTableBytes && dequeue()) {
+            if (m_callback) m_callback({m_packet.data(), m_packet.size()}, true);
+            delivered += m_packet.size();
+        }
+    }
+public:
+    explicit MSC_Reed_Solomon_Data_Packet_Processor(std::shared_ptr<Context> ctx = nullptr) : m_ctx(ctx ? ctx : default_context()) {}
+    void SetCallback(const Callback& callback) { m_callback = callback; }
+    void SetCallback(Callback&& callback) { m_callback = std::move(callback); }
+    size_t ReadPacket(span<const uint8_t> buf) {
+        if (buf.size() < kFecHeader) return buf.size();
+        const uint16_t address = uint16_t((uint16_t(buf[0] & 3u) << 8) | buf[1]);
+        const uint8_t counter = uint8_t((buf[0] >> 2) & 0xFu);
+        const bool is_fec = address == kFecAddress;
+        const uint8_t length_id = is_fec ? uint8_t(0) : uint8_t(buf[0] >> 6);   // the length field of a FEC packet is not trusted
+        const size_t n = length_of(length_id);
+        if (buf.size() < n) return buf.size();
+        enqueue(buf.first(n), length_id);
+        if (!is_fec) return n;
+        if (int(counter) != m_fec_seen + 1) {      // sets count 0..8; anything else abandons the set
+            m_fec_seen = -1;
+            flush_uncorrected();
+            return n;
+        }
+        m_fec_seen = int(counter);
+        if (size_t(counter) + 1 != kFecPackets) return n;
+        if (m_fill == kCapacity) correct_and_flush(); else flush_uncorrected();
+        m_fec_seen = -1;
+        m_front = m_back = m_fill = 0;
+        return n;
     }
 };
 

@@ -346,6 +346,37 @@ def rs_encode(data: Sequence[int], nroots: int = 10) -> List[int]:
     return rem
 
 
+def packet_fec_set(rng: np.random.Generator, lengths: Optional[Sequence[int]] = None) -> List[np.ndarray]:
+    """One complete packet-mode FEC set (ETSI EN 300 401 5.3.5): data packets filling the 2256-byte application data table,
+    then the nine 24-byte FEC packets (address 1022, counters 0..8) that carry the RS(204,188) parity of its 12 rows."""
+    if lengths is None:
+        lengths, left = [], 2256
+        while left > 0:
+            n = int(rng.choice([x for x in (24, 48, 72, 96) if x <= left]))
+            lengths.append(n)
+            left -= n
+    assert sum(lengths) == 2256
+    packets = []
+    for i, n in enumerate(lengths):
+        p = rng.integers(0, 256, size=n, dtype=np.uint8)
+        address = int(rng.integers(1, 1000))
+        p[0] = ((n // 24 - 1) << 6) | ((i & 3) << 4) | (int(rng.integers(0, 4)) << 2) | (address >> 8)
+        p[1] = address & 0xFF
+        packets.append(p)
+    table = np.concatenate(packets)
+    parity = np.zeros(192, dtype=np.uint8)
+    for y in range(12):
+        parity[y::12] = rs_encode([int(v) for v in table[y::12]], 16)
+    for i in range(9):
+        p = np.zeros(24, dtype=np.uint8)
+        p[0] = (i << 2) | 0x03
+        p[1] = 0xFE
+        n = 22 if i < 8 else 16
+        p[2:2 + n] = parity[22 * i:22 * i + n]
+        packets.append(p)
+    return packets
+
+
 def build_superframe(bitrate_kbps: int, rng: np.random.Generator, dac_rate: int = 1, sbr: int = 1,
                      stereo: int = 1, ps: int = 0, mpeg: int = 0) -> np.ndarray:
     """One DAB+ audio superframe (5 logical frames) with valid fire code, AU CRCs and RS parity."""

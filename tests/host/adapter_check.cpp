@@ -122,6 +122,26 @@ static void run_rs(Reader& in, Writer& out) {
     }
 }
 
+// n_bufs; per buffer: len, bytes  ->  per buffer: consumed, n_callbacks, per callback {len, is_corrected, bytes}
+static void run_pktfec(Reader& in, Writer& out) {
+    MSC_Reed_Solomon_Data_Packet_Processor proc;
+    Writer* sink = &out;
+    int fired = 0;
+    Writer tmp;
+    proc.SetCallback([&](span<const uint8_t> pkt, bool corrected) {
+        fired++;
+        tmp.i32(int32_t(pkt.size())); tmp.i32(corrected ? 1 : 0); tmp.bytes(pkt.data(), pkt.size());
+    });
+    const int n = in.i32();
+    for (int i = 0; i < n; i++) {
+        const int len = in.i32();
+        const uint8_t* p = in.bytes(size_t(len));
+        fired = 0; tmp.buf.clear();
+        const size_t used = proc.ReadPacket({p, size_t(len)});
+        sink->i32(int32_t(used)); sink->i32(fired); sink->bytes(tmp.buf.data(), tmp.buf.size());
+    }
+}
+
 struct EventSink {
     Writer& out;
     int n = 0;
@@ -259,7 +279,7 @@ static void run_taps(Reader& in, Writer& out) {
 }
 
 int main(int argc, char** argv) {
-    if (argc != 4) { std::cerr << "usage: adapter_check <viterbi|fic|msc|mscpool|rs|aac|radio|selfcfg|taps> in.bin out.bin\n"; return 1; }
+    if (argc != 4) { std::cerr << "usage: adapter_check <viterbi|fic|msc|mscpool|rs|pktfec|aac|radio|selfcfg|taps> in.bin out.bin\n"; return 1; }
     try {
         Reader in(argv[2]);
         Writer out;
@@ -269,6 +289,7 @@ int main(int argc, char** argv) {
         else if (what == "msc") run_msc(in, out);
         else if (what == "rs") run_rs(in, out);
         else if (what == "aac") run_aac(in, out);
+        else if (what == "pktfec") run_pktfec(in, out);
         else if (what == "radio") run_radio(in, out);
         else if (what == "selfcfg") run_selfcfg(in, out);
         else if (what == "mscpool") run_mscpool(in, out);

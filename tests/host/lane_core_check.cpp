@@ -19,7 +19,7 @@ static void lane_decode(const int8_t* soft4, uint32_t n_steps, uint8_t* out, uin
     vl_reset(S);
     const uint32_t padded = ((n_steps + VL_UNROLL - 1) / VL_UNROLL) * VL_UNROLL;
     std::vector<uint32_t> d0(padded), d1(padded);
-    uint64_t final_err = 0;
+    uint32_t final_rel = 0;
     for (uint32_t t0 = 0; t0 < padded; t0 += VL_UNROLL) {
         uint32_t w[VL_UNROLL], dec[2 * VL_UNROLL];
         for (uint32_t k = 0; k < VL_UNROLL; k++) {
@@ -27,10 +27,10 @@ static void lane_decode(const int8_t* soft4, uint32_t n_steps, uint8_t* out, uin
             if (t0 + k < n_steps) memcpy(&w[k], soft4 + 4 * size_t(t0 + k), 4);
         }
         if (no_clamp) S.CL = 0x7FFF7FFFu;
-        vl_step5(S, w, t0, n_steps, dec, final_err, KC);
+        vl_step5(S, w, t0, n_steps, dec, final_rel, KC);
         for (uint32_t k = 0; k < VL_UNROLL; k++) { d0[t0 + k] = dec[2 * k]; d1[t0 + k] = dec[2 * k + 1]; }
     }
-    *err = final_err;
+    *err = vl_final_error(S, final_rel);
     // ViterbiDecoder_Core::chainback from state 0: decoded bit b comes from the decision word of step b + 6
     memset(out, 0, n_out_bytes);
     uint32_t state = 0;
