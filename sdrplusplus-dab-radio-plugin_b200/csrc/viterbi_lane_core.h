@@ -257,3 +257,21 @@ VL_HD uint32_t vl_decision(const uint32_t d0, const uint32_t d1, const uint32_t 
     const uint32_t pos = ((j >> (k + 1u)) << k) | (j & ((1u << k) - 1u)) | (((j >> k) & 1u) << 4);
     return (word >> pos) & 1u;
 }
+
+// The same walk with the survivor state kept in the top six bits of a 32-bit history word h (state = h >> 26; the history is
+// also the word of decoded bits under construction, newest bit on top): one traceback step is
+//   h' = (h >> 1) | (decision(state) << 31).
+// With j = h >> 27 the position above is (j with bit k moved to bit 4) = ((h >> 28) & ~m) | ((h >> 27) & m) | ((h >> (23 + k)) & 16),
+// m = 2^k - 1: three shifts and two 3-input logic operations; only bit 0 of the shifted decision word enters the funnel shift.
+template <uint32_t K>
+VL_HD uint32_t vl_traceback_step(const uint32_t d0, const uint32_t d1, const uint32_t h) {
+    const uint32_t word = (h & (1u << 26)) ? d1 : d0;
+    constexpr uint32_t m = (1u << K) - 1u;
+    const uint32_t pos = (((h >> 28) & ~m) | ((h >> 27) & m) | ((h >> (23u + K)) & 16u)) & 31u;
+    const uint32_t x = word >> pos;
+#if defined(VL_DEVICE_CODE)
+    return __funnelshift_r(h, x, 1u);
+#else
+    return (h >> 1) | (x << 31);
+#endif
+}

@@ -300,14 +300,52 @@ __device__ __forceinline__ void vl_emit_word(uint8_t* __restrict__ out, const ui
 
 // Whole-block traceback from state 0 (viterbi_decoder_core.h:214-236): decoded bit b comes from the decision word of
 // step b + 6.  All lanes walk the same rows (coalesced 256 B loads, two batches of rows in flight); a lane joins when the
-// walk reaches the last decision word it needs.  Then energy dispersal (additive_scrambler.h:10-36) and the FIB CRCs.
+// walk reaches the last decision word it needs (its history word stays 0 = state 0 until then).  The survivor state is the
+// top of the history word h, which is at the same time the word of decoded bits being assembled (vl_traceback_step): 13
+// instructions per step where the first version, with separate state and accumulator and a generic bit position, took 45.
+// Rows 5..0 are walked as well (their bits are never emitted): no lower bound to test.
+// Then energy dispersal (additive_scrambler.h:10-36) and the FIB CRCs.
+// ALL: every lane that holds a trellis joins at the first row (the usual group: equal lengths), so the step needs no test
+template <uint32_t K, bool ALL>
+__device__ __forceinline__ void vl_tb_row(const uint2 d, const uint32_t t, const uint32_t join_t, uint32_t& h, const uint32_t n_out_bytes, const uint32_t flags,
+                                          uint8_t* __restrict__ const out, const uint32_t* __restrict__ prbs_words) {
+    if (ALL || t < join_t) h = vl_traceback_step<K>(d.x, d.y, h);
+    if (((t - 6u) & 31u) == 0u && t >= 6u) {      // warp-uniform: 32 bits complete, bit b = t - 6 on top
+        const uint32_t widx = (t - 6u) >> 5;
+        uint32_t v = h;
+        if (flags & VJ_DESCRAMBLE) v ^= prbs_words[widx];
+        if (t < join_t) vl_emit_word(out, n_out_bytes, widx, v);
+    }
+}
+
+template <uint32_t VL_TB_BLOCK, bool ALL>
+__device__ __forceinline__ void vl_tb_block(const uint2 (&cur)[VL_TB_BLOCK], const uint32_t t0, const uint32_t join_t, uint32_t& h, const uint32_t n_out_bytes,
+                                            const uint32_t flags, uint8_t* __restrict__ const out, const uint32_t* __restrict__ prbs_words) {
+#pragma unroll
+    for (int r = int(VL_TB_BLOCK) - 1; r >= 0; --r) {
+        switch (r % VL_UNROLL) {
+        case 0: vl_tb_row<0, ALL>(cur[r], t0 + uint32_t(r), join_t, h, n_out_bytes, flags, out, prbs_words); break;
+        case 1: vl_tb_row<1, ALL>(cur[r], t0 + uint32_t(r), join_t, h, n_out_bytes, flags, out, prbs_words); break;
+        case 2: vl_tb_row<2, ALL>(cur[r], t0 + uint32_t(r), join_t, h, n_out_bytes, flags, out, prbs_words); break;
+        case 3: vl_tb_row<3, ALL>(cur[r], t0 + uint32_t(r), join_t, h, n_out_bytes, flags, out, prbs_words); break;
+        default: vl_tb_row<4, ALL>(cur[r], t0 + uint32_t(r), join_t, h, n_out_bytes, flags, out, prbs_words); break;
+        }
+    }
+}
+
 template <uint32_t VL_TB_BLOCK>   // traceback rows fetched per batch (multiple of VL_UNROLL), two batches in flight
 __device__ __forceinline__ void vl_traceback(const uint2* __restrict__ dec, const VitJobDev* __restrict__ J, const bool have, const uint32_t n_out_bytes,
                                              const uint32_t flags, uint8_t* __restrict__ const out, const uint32_t* __restrict__ prbs_words) {
+    static_assert(VL_TB_BLOCK % VL_UNROLL == 0, "the layout index of a row must be a compile-time constant");
     const uint32_t nbits = n_out_bytes * 8u;
-    const uint32_t top = __reduce_max_sync(FULL_MASK, nbits);      // rows top+5 .. 6 are walked
+    const uint32_t top = __reduce_max_sync(FULL_MASK, nbits);      // rows top+5 .. 0 are walked
     if (top != 0u) {
-        uint32_t state = 0, acc = 0;
+        const uint32_t join_t = nbits != 0u ? nbits + 6u : 0u;
+        // the usual group: every trellis has the same length, all lanes join at row top + 5.  Only the first block, which also
+        // holds rows above it (padded steps of the forward pass), then needs the per-lane test.  Lanes without a trellis walk
+        // along without storing anything.
+        const bool same = __all_sync(FULL_MASK, join_t == 0u || join_t == top + 6u);
+        uint32_t h = 0;
         const int first_block = int((top + 5u) / VL_TB_BLOCK);
         uint2 cur[VL_TB_BLOCK];
 #pragma unroll
@@ -319,23 +357,9 @@ __device__ __forceinline__ void vl_traceback(const uint2* __restrict__ dec, cons
 #pragma unroll
                 for (int r = 0; r < int(VL_TB_BLOCK); r++) nx[r] = dec[size_t(uint32_t(blk - 1) * VL_TB_BLOCK + r) * 32u];
             }
-#pragma unroll
-            for (int r = int(VL_TB_BLOCK) - 1; r >= 0; --r) {
-                const uint32_t t = uint32_t(blk) * VL_TB_BLOCK + uint32_t(r);
-                if (t >= 6u && t < nbits + 6u) {
-                    const uint32_t b = t - 6u;
-                    const uint32_t bit = vl_decision(cur[r].x, cur[r].y, state, uint32_t(r) % VL_UNROLL);
-                    state = (state >> 1) | (bit << 5);
-                    acc = (acc >> 1) | (bit << 31);
-                    if ((b & 31u) == 0u) {
-                        const uint32_t widx = b >> 5;
-                        uint32_t v = acc;
-                        if (flags & VJ_DESCRAMBLE) v ^= prbs_words[widx];
-                        vl_emit_word(out, n_out_bytes, widx, v);
-                        acc = 0;
-                    }
-                }
-            }
+            const uint32_t t0 = uint32_t(blk) * VL_TB_BLOCK;
+            if (same && blk != first_block) vl_tb_block<VL_TB_BLOCK, true>(cur, t0, join_t, h, n_out_bytes, flags, out, prbs_words);
+            else vl_tb_block<VL_TB_BLOCK, false>(cur, t0, join_t, h, n_out_bytes, flags, out, prbs_words);
             if (blk > 0) {
 #pragma unroll
                 for (int r = 0; r < int(VL_TB_BLOCK); r++) cur[r] = nx[r];

@@ -32,13 +32,22 @@ static void lane_decode(const int8_t* soft4, uint32_t n_steps, uint8_t* out, uin
     }
     *err = vl_final_error(S, final_rel);
     // ViterbiDecoder_Core::chainback from state 0: decoded bit b comes from the decision word of step b + 6
+    // twice: with the generic bit position (vl_decision) and with the history-word step the kernel uses (vl_traceback_step)
     memset(out, 0, n_out_bytes);
-    uint32_t state = 0;
+    uint32_t state = 0, h = 0;
     for (int b = int(n_out_bytes) * 8 - 1; b >= 0; --b) {
         const uint32_t t = uint32_t(b) + 6u;
         const uint32_t bit = vl_decision(d0[t], d1[t], state, t % VL_UNROLL);
         state = (state >> 1) | (bit << 5);
-        out[b >> 3] |= uint8_t(bit << (7 - (b & 7)));
+        switch (t % VL_UNROLL) {
+        case 0: h = vl_traceback_step<0>(d0[t], d1[t], h); break;
+        case 1: h = vl_traceback_step<1>(d0[t], d1[t], h); break;
+        case 2: h = vl_traceback_step<2>(d0[t], d1[t], h); break;
+        case 3: h = vl_traceback_step<3>(d0[t], d1[t], h); break;
+        default: h = vl_traceback_step<4>(d0[t], d1[t], h); break;
+        }
+        if ((h >> 26) != state) { *err = ~0ull; return; }    // the two walks disagree: reported as a path-error mismatch
+        out[b >> 3] |= uint8_t((h >> 31) << (7 - (b & 7)));
     }
 }
 
