@@ -437,8 +437,13 @@ static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, 
         }
         k_vit_plan<<<1, 32, 0, ctx->stream>>>(plan, ctx->vl_mode, ctx->vl_min_jobs, rows, groups);
         k_vit_scatter<<<nb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, plan, ctx->d_vllist.as<uint32_t>());
-        k_vit_prep<<<(groups + VP_WARPS - 1u) / VP_WARPS, VP_WARPS * 32, VP_SMEM_BYTES, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(), ctx->d_vlsym.as<uint32_t>(),
-                                                                                               ctx->chan.geom);
+        // enough warps to fill the GPU: a group's steps are split over up to eight warps
+        uint32_t split = 1u;
+        while (split < 8u && groups * split * 2u <= uint32_t(ctx->num_sms) * 48u) split *= 2u;
+        if (groups * split < uint32_t(ctx->num_sms) * 48u && split < 8u) split *= 2u;
+        if (const char* e = getenv("DABGPU_PREP_SPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 16) split = uint32_t(v); }   // tuning knob
+        k_vit_prep<<<(groups * split + VP_WARPS - 1u) / VP_WARPS, VP_WARPS * 32, VP_SMEM_BYTES, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(),
+                                                                                                       ctx->d_vlsym.as<uint32_t>(), ctx->chan.geom, split);
         ctx->prof.end(ctx->stream);
         ctx->prof.begin(PROF_VITERBI, ctx->stream);
         if (!lanes_wide) {

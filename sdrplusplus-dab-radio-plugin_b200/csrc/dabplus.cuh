@@ -122,6 +122,8 @@ struct DpShared {
     // branch-free x * alpha^r for the syndrome loop: gf_exz[gf_lgx[x] + r] with log(0) mapped past the end of the exp table
     uint16_t gf_lgx[256];
     uint8_t gf_exz[528];
+    // x -> x * alpha^r for the roots r = 2..9 of the DAB+ code: one lookup per Horner step (root 0 needs none, root 1 is a shift)
+    uint8_t gf_mulr[8][256];
     __align__(16) uint8_t sfbuf[DP_WARPS][DP_SF_SMEM];
 };
 
@@ -134,6 +136,10 @@ __device__ __forceinline__ void dp_load_shared(DpShared& sh) {
         sh.gf_lgx[i] = i ? uint16_t(c_gf_log[i]) : uint16_t(512);
     }
     for (int i = threadIdx.x; i < 528; i += blockDim.x) sh.gf_exz[i] = (i < 510) ? c_gf_exp[i] : uint8_t(0);
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) {
+        const int r = 2 + (i >> 8), x = i & 255;
+        sh.gf_mulr[i >> 8][x] = x ? c_gf_exp[c_gf_log[x] + r] : uint8_t(0);
+    }
     __syncthreads();
 }
 
@@ -141,6 +147,32 @@ __device__ __forceinline__ uint16_t crc16_tab(const uint16_t* tab, const uint8_t
     uint32_t crc = init;
     for (int i = 0; i < n; i++) crc = ((crc << 8) ^ tab[((crc >> 8) ^ p[i]) & 0xFFu]) & 0xFFFFu;
     return uint16_t(crc ^ xorout);
+}
+
+// a * b in GF(2)[x] modulo the CCITT polynomial x^16 + x^12 + x^5 + 1
+__device__ __forceinline__ uint32_t crc_mulmod(const uint32_t a, const uint32_t b) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 15; i >= 0; i--) {
+        r <<= 1;
+        if (r & 0x10000u) r ^= 0x11021u;
+        if ((b >> i) & 1u) r ^= a;
+    }
+    return r;
+}
+
+// CRC16-CCITT (init 0xFFFF, final inversion; crc.h:46-67) of n bytes by a whole warp: lane l runs the table loop over its chunk
+// of ceil(n / 32) bytes (lane 0 carries the initial value), weighs the result with x^(8 * bytes that follow) and the lanes XOR
+// their shares.  A 300-byte access unit is a dependent chain of 10 table steps instead of 300.  Every lane returns the CRC.
+__device__ __forceinline__ uint16_t crc16_ccitt_warp(const uint16_t* tab, const uint8_t* p, const int n, const uint32_t lane) {
+    const int c = (n + 31) >> 5;
+    const int b0 = min(n, int(lane) * c), b1 = min(n, b0 + c);
+    uint32_t crc = (lane == 0u) ? 0xFFFFu : 0u;
+    for (int k = b0; k < b1; k++) crc = ((crc << 8) ^ tab[((crc >> 8) ^ p[k]) & 0xFFu]) & 0xFFFFu;
+    uint32_t share = (b1 > b0 || lane == 0u) ? crc_mulmod(crc, g_crc_xp8[n - b1]) : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) share ^= __shfl_xor_sync(FULL_MASK, share, o);
+    return uint16_t(share ^ 0xFFFFu);
 }
 
 __device__ __forceinline__ void dp_emit(DabPlusEvent* ev, int32_t* n_ev, int type, int a, int b, int c, int d, int off, int len) {
@@ -178,30 +210,45 @@ __device__ void dp_superframe(DpShared& sh, uint8_t* sf_global, uint8_t* sf_out,
         for (int i = int(lane); i < total / 4; i += 32) dst[i] = src[i];
         __syncwarp();
     }
-    // ReedSolomonDecode (aac_frame_processor.cpp:322-362): codeword i = bytes {i + j*N}.  Eight codewords per pass, four
-    // lanes per codeword: lane part p evaluates the syndromes of roots p, p+4, p+8, the leader lane (p = 0) collects them.
+    // ReedSolomonDecode (aac_frame_processor.cpp:322-362): codeword i = bytes {i + j*N}.  Eight codewords per pass, four lanes per
+    // codeword: lane part q runs the Horner recurrences of ALL ten roots (reed_solomon_decoder.cpp:223-240) over bytes 30q .. 30q+29
+    // -- ten independent chains of 30 steps, one table lookup per step (x -> x * alpha^r) -- then moves its partial syndromes to
+    // the end of the codeword (times alpha^(30 r (3 - q))) and the four lanes XOR their shares.  The first version ran three
+    // chains of 120 steps with two dependent lookups each per lane: the kernel was bound by that latency.
     for (int base = 0; base < N; base += 8) {
         const int i = base + int(lane >> 2);
         const int part = int(lane & 3u);
-        uint8_t Sp[3] = {0, 0, 0};
-        if (i < N) {
-            Sp[0] = Sp[1] = Sp[2] = sf[i];
-            for (int j = 1; j < 120; j++) {
-                const uint8_t d = sf[i + j * N];
+        uint32_t P[10];
 #pragma unroll
-                for (int q = 0; q < 3; q++) {
-                    const int r = part + 4 * q;   // root index; r >= 10 is computed but ignored
-                    Sp[q] = uint8_t(d ^ sh.gf_exz[sh.gf_lgx[Sp[q]] + r]);   // Horner step s = s * alpha^r + d (reed_solomon_decoder.cpp:223-240)
+        for (int r = 0; r < 10; r++) P[r] = 0u;
+        if (i < N) {
+            const uint8_t* p = sf + i + 30 * part * N;
+#pragma unroll 2
+            for (int j = 0; j < 30; j++) {
+                const uint32_t d = p[j * N];
+                P[0] ^= d;
+                P[1] = (((P[1] << 1) ^ ((P[1] & 0x80u) ? 0x11Du : 0u)) ^ d) & 0xFFu;
+#pragma unroll
+                for (int r = 2; r < 10; r++) P[r] = uint32_t(sh.gf_mulr[r - 2][P[r]]) ^ d;
+            }
+            if (part < 3) {
+#pragma unroll
+                for (int r = 1; r < 10; r++) {
+                    const int e = (30 * r * (3 - part)) % 255;
+                    P[r] = P[r] ? uint32_t(sh.gf_ex[int(sh.gf_lg[P[r]]) + e]) : 0u;
                 }
             }
         }
+        uint32_t pk0 = P[0] | (P[1] << 8) | (P[2] << 16) | (P[3] << 24), pk1 = P[4] | (P[5] << 8) | (P[6] << 16) | (P[7] << 24), pk2 = P[8] | (P[9] << 8);
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            pk0 ^= __shfl_xor_sync(FULL_MASK, pk0, o);
+            pk1 ^= __shfl_xor_sync(FULL_MASK, pk1, o);
+            pk2 ^= __shfl_xor_sync(FULL_MASK, pk2, o);
+        }
         uint8_t S[10];
 #pragma unroll
-        for (int r = 0; r < 10; r++) {
-            const uint32_t packed = uint32_t(Sp[0]) | (uint32_t(Sp[1]) << 8) | (uint32_t(Sp[2]) << 16);
-            const uint32_t v = __shfl_sync(FULL_MASK, packed, (lane & ~3u) + uint32_t(r & 3));
-            S[r] = uint8_t(v >> (8 * (r >> 2)));
-        }
+        for (int r = 0; r < 10; r++) S[r] = uint8_t((r < 4 ? pk0 : r < 8 ? pk1 : pk2) >> (8 * (r & 3)));
         int cnt = 0;
         uint8_t loc[10], xv[10], ap[10];
         const bool leader = (part == 0) && (i < N);
@@ -258,39 +305,28 @@ __device__ void dp_superframe(DpShared& sh, uint8_t* sf_global, uint8_t* sf_out,
     const int nb_tbl = dp_read_au_start(sf + 3, &au_start[1], num_aus - 1);
     au_start[num_aus] = uint16_t(110 * N);
     au_start[0] = uint16_t(3 + nb_tbl);
-    // per-AU CRC in parallel (lane i < num_aus), events emitted in order by lane 0
-    int au_state = 0;   // 0 = stop (bounds), 1 = crc error, 2 = ok
-    uint32_t crc_pair = 0;
-    if (int(lane) < num_aus) {
-        const int nb_au = int(au_start[lane + 1]) - int(au_start[lane]);
-        const int nb_data = nb_au - 2;
-        if (!(nb_data < 0 || int(au_start[lane + 1]) >= total)) {
-            const uint8_t* au = sf + au_start[lane];
-            const uint16_t rx = uint16_t((uint16_t(au[nb_data]) << 8) | au[nb_data + 1]);
-            const uint16_t pred = crc16_tab(sh.crc_ccitt, au, nb_data, 0xFFFF, 0xFFFF);
-            au_state = (rx == pred) ? 2 : 1;
-            crc_pair = (uint32_t(rx) << 16) | pred;
-        }
+    // access units in order (aac_frame_processor.cpp:281-320): bounds, CRC by the whole warp, events from lane 0
+    if (lane == 0) {
+        st.desync = 0; st.synced = 1;
+        const int surround = (mpeg == 0) ? 0 : (mpeg == 1) ? 1 : (mpeg == 2) ? 2 : (mpeg == 7) ? 3 : 4;
+        dp_emit(ev, n_ev, DABGPU_EV_SUPERFRAME_HEADER, dac_rate ? 48000 : 32000, (ps ? 1 : 0) | (sbr ? 2 : 0) | (ch ? 4 : 0), surround, 0, 0, 0);
+        atomicAdd(&counters[CNT_SF_OK], 1ull);
     }
-    for (int i = 0; i < 6; i++) {
-        const int s_i = __shfl_sync(FULL_MASK, au_state, i);
-        const uint32_t c_i = __shfl_sync(FULL_MASK, crc_pair, i);
-        if (lane == 0 && i < num_aus) {
-            if (i == 0) {
-                st.desync = 0; st.synced = 1;
-                const int surround = (mpeg == 0) ? 0 : (mpeg == 1) ? 1 : (mpeg == 2) ? 2 : (mpeg == 7) ? 3 : 4;
-                dp_emit(ev, n_ev, DABGPU_EV_SUPERFRAME_HEADER, dac_rate ? 48000 : 32000, (ps ? 1 : 0) | (sbr ? 2 : 0) | (ch ? 4 : 0), surround, 0, 0, 0);
-                atomicAdd(&counters[CNT_SF_OK], 1ull);
-            }
-            if (s_i == 1) {
-                dp_emit(ev, n_ev, DABGPU_EV_AU_CRC_ERROR, i, num_aus, int(c_i >> 16), int(c_i & 0xFFFFu), 0, 0);
+    for (int i = 0; i < num_aus; i++) {
+        const int nb_data = int(au_start[i + 1]) - int(au_start[i]) - 2;
+        if (nb_data < 0 || int(au_start[i + 1]) >= total) break;   // "access unit out of bounds" => return (aac_frame_processor.cpp:289-296)
+        const uint8_t* au = sf + au_start[i];
+        const uint16_t rx = uint16_t((uint16_t(au[nb_data]) << 8) | au[nb_data + 1]);
+        const uint16_t pred = crc16_ccitt_warp(sh.crc_ccitt, au, nb_data, lane);
+        if (lane == 0) {
+            if (rx != pred) {
+                dp_emit(ev, n_ev, DABGPU_EV_AU_CRC_ERROR, i, num_aus, int(rx), int(pred), 0, 0);
                 atomicAdd(&counters[CNT_AU_CRC_FAIL], 1ull);
-            } else if (s_i == 2) {
-                dp_emit(ev, n_ev, DABGPU_EV_ACCESS_UNIT, i, num_aus, 0, 0, sf_base + int(au_start[i]), int(au_start[i + 1]) - int(au_start[i]) - 2);
+            } else {
+                dp_emit(ev, n_ev, DABGPU_EV_ACCESS_UNIT, i, num_aus, 0, 0, sf_base + int(au_start[i]), nb_data);
                 atomicAdd(&counters[CNT_AU_OK], 1ull);
             }
         }
-        if (i < num_aus && s_i == 0) break;   // "access unit out of bounds" => return (aac_frame_processor.cpp:289-296)
     }
 }
 

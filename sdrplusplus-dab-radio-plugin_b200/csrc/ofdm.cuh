@@ -278,10 +278,34 @@ __device__ __forceinline__ void ctl_l1_batch(const OfdmDev& D, const int s, cons
         if (w < nb) {
             const int i0 = (tid & 1) * half, i1 = min(count, i0 + half);
             const unsigned long long base = a0 + (unsigned long long)w * (unsigned long long)stride;
+            const unsigned long long pos = (base + (unsigned long long)i0) & D.ring_mask;
+            if (D.iq_format == DABGPU_IQ_U8 && count == 100 && (D.ring_mask == ~0ull || pos + 50ull <= D.ring_mask + 1ull)) {
+                // the default window (signal_l1.nb_samples = 100) on u8 input: the 100 bytes of this lane's half are fetched as 26
+                // aligned words that are all in flight at once -- one memory round trip where the sample loop below makes five
+                // dependent ones -- and summed in the same order
+                const uintptr_t a = reinterpret_cast<uintptr_t>(D.ring) + 2u * ((unsigned long long)s * D.ring_stride + pos);
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+                const bool odd = (a & 2u) != 0u;
+                uint32_t wd[26];
+#pragma unroll
+                for (int k = 0; k < 25; k++) wd[k] = __ldg(q + k);
+                wd[25] = odd ? __ldg(q + 25) : 0u;
+#pragma unroll
+                for (int k = 0; k < 25; k++) {
+                    const uint32_t r = odd ? __funnelshift_r(wd[k], wd[k + 1], 16) : wd[k];
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; h2++) {
+                        const float x = __fmul_rn(__fsub_rn(float((r >> (16 * h2)) & 0xFFu), 127.5f), 1.0f / 127.5f);
+                        const float y = __fmul_rn(__fsub_rn(float((r >> (16 * h2 + 8)) & 0xFFu), 127.5f), 1.0f / 127.5f);
+                        acc += fabsf(x) + fabsf(y);
+                    }
+                }
+            } else {
 #pragma unroll 10
-            for (int i = i0; i < i1; i++) {
-                const float2 v = ofdm_ring_sample(D, s, base + i);
-                acc += fabsf(v.x) + fabsf(v.y);
+                for (int i = i0; i < i1; i++) {
+                    const float2 v = ofdm_ring_sample(D, s, base + i);
+                    acc += fabsf(v.x) + fabsf(v.y);
+                }
             }
         }
         acc += __shfl_xor_sync(FULL_MASK, acc, 1);
@@ -290,7 +314,7 @@ __device__ __forceinline__ void ctl_l1_batch(const OfdmDev& D, const int s, cons
 }
 
 template <int N>
-__global__ void __launch_bounds__(N / 8, (N == 2048) ? 2 : 4)   // 2048: <= 128 registers so that two CTAs (streams) share an SM
+__global__ void __launch_bounds__(N / 8, (N == 2048) ? 3 : 4)   // 2048: 80 registers, three CTAs (streams) per SM: 0.317 -> 0.283 ms per 1024-stream step; four (64 registers) spill more than they hide (0.284)
 k_ofdm_ctl(const OfdmDev D, const int first_stream, const int n_new_samples, const int block_size, const int is_first) {
     constexpr int NT = N / 8;
     constexpr int NP = N + N / 8;
@@ -301,8 +325,13 @@ k_ofdm_ctl(const OfdmDev D, const int first_stream, const int n_new_samples, con
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const OfdmGeom& g = D.g;
     OfdmStream& st = sh.st;
+    // the stream record and the frame's cyclic-prefix phase errors come in with one coalesced round trip each (thread 0 alone
+    // took a dependent load per field and per symbol while the rest of the CTA waited at the first barrier: a fifth of the kernel)
+    static_assert(sizeof(OfdmStream) % 4 == 0 && sizeof(OfdmStream) <= 4 * NT, "stream record is copied one word per thread");
+    if (tid < int(sizeof(OfdmStream) / 4)) reinterpret_cast<uint32_t*>(&sh.st)[tid] = reinterpret_cast<const uint32_t*>(D.st + s)[tid];
+    for (int l = tid; l < g.L; l += NT) sh.l1[l] = D.phase_err[size_t(s) * g.L + l];   // L <= 153 < OFDM_L1_BATCH
+    __syncthreads();
     if (tid == 0) {
-        st = D.st[s];
         if (is_first) {
             st.push_end += (unsigned long long)n_new_samples;
             st.block_size = block_size > 0 ? block_size : n_new_samples;
@@ -310,9 +339,8 @@ k_ofdm_ctl(const OfdmDev D, const int first_stream, const int n_new_samples, con
         }
         if (st.pending == 1) {
             // coordinator (ofdm_demodulator.cpp:608-635): average CP phase -> fine frequency, then emit the frame
-            const float* pe = D.phase_err + size_t(s) * g.L;
             float total = 0.0f;
-            for (int l = 0; l < g.L; l++) total += pe[l];
+            for (int l = 0; l < g.L; l++) total += sh.l1[l];
             const float avg = total / float(g.L);
             const float err = (1.0f / float(N)) * avg / (2.0f * 3.14159265358979323846f);
             ctl_update_fine(st, N, -D.cfg.fine_freq_update_beta * err);
@@ -619,7 +647,7 @@ k_ofdm_ctl(const OfdmDev D, const int first_stream, const int n_new_samples, con
         }
     }
     __syncthreads();
-    if (tid == 0) D.st[s] = st;
+    if (tid < int(sizeof(OfdmStream) / 4)) reinterpret_cast<uint32_t*>(D.st + s)[tid] = reinterpret_cast<const uint32_t*>(&sh.st)[tid];
 }
 
 // Packs the newest frame of every stream that produced one in the last call into a contiguous staging buffer.

@@ -34,6 +34,11 @@ __constant__ uint32_t c_branch[32];
 __constant__ uint16_t c_crc_ccitt[256];
 __constant__ uint16_t c_crc_fire[256];
 
+// x^(8m) mod the CCITT polynomial, m = 0..2047: the weight of a partial CRC that is followed by m more bytes (k_dabplus splits
+// the CRC of an access unit over the 32 lanes of a warp).  In global memory: every lane reads a different entry.
+#define CRC_XP8_ENTRIES 2048
+__device__ uint16_t g_crc_xp8[CRC_XP8_ENTRIES];
+
 // Time de-interleaver: age (0 = newest CIF) of the CIF that carries bit i of the oldest complete
 // logical frame, i mod 16.  Reference: dab/msc/cif_deinterleaver.cpp:8-11, 62-68 (15 - offset).
 __constant__ uint8_t c_ti_age[16];
@@ -90,6 +95,15 @@ static int upload_constant_tables() {
     }
     CUDA_TRY(cudaMemcpyToSymbol(c_crc_ccitt, t1, sizeof(t1)));
     CUDA_TRY(cudaMemcpyToSymbol(c_crc_fire, t2, sizeof(t2)));
+    {
+        static uint16_t xp[CRC_XP8_ENTRIES];
+        uint16_t v = 1;     // the polynomial "1"; appending a zero byte multiplies by x^8: one table step
+        for (int m = 0; m < CRC_XP8_ENTRIES; m++) {
+            xp[m] = v;
+            v = uint16_t((v << 8) ^ t1[v >> 8]);
+        }
+        CUDA_TRY(cudaMemcpyToSymbol(g_crc_xp8, xp, sizeof(xp)));
+    }
 
     static const uint8_t TI[16] = {0, 8, 4, 12, 2, 10, 6, 14, 1, 9, 5, 13, 3, 11, 7, 15};
     uint8_t age[16];

@@ -126,10 +126,12 @@ __device__ __forceinline__ void vl_locate(const VlPlan* __restrict__ plan, const
 // The first version fetched single bytes through the 16-way strided gather of a natural-order frame ring (one dependent L2
 // round trip per step, 63 instructions per step and lane, every DRAM sector read six times).
 // ---------------------------------------------------------------------------------------------------------------------------
-#define VP_TILE 32u
-#define VP_WARPS 4u
+#ifndef VP_UNIT
 #define VP_UNIT 128u           // bytes per refill
-#define VP_WORDS 64u           // window of 2 units = 256 symbols per lane
+#endif
+#define VP_TILE (VP_UNIT / 4u) // steps per tile: a tile reads at most one unit's worth of symbols from the position of its first step
+#define VP_WARPS 4u
+#define VP_WORDS (VP_UNIT / 2u) // window of 2 units per lane, in words
 #define VP_MIRROR 9u
 #define VP_SMEM_BYTES (size_t(VP_WARPS) * (VP_WORDS + VP_MIRROR) * 32u * sizeof(uint32_t))
 
@@ -161,11 +163,16 @@ __device__ __forceinline__ uint32_t prep_word(const uint32_t (*L)[32], const uin
     return __funnelshift_r(L[wi][lane], L[wi + 1u][lane], lam * 8u) & prep_mask(cnt);   // the shift uses the low 5 bits: (lam & 3) * 8
 }
 
+// `split` warps share a group: each takes a contiguous range of tiles.  A group alone keeps one warp busy for 1542 steps of a
+// dependent refill -> de-puncture -> store chain, and a call has only as many groups as a quarter of the warps the GPU can
+// hold; the step -> input index map (prep_in_index) is random access, so the walk can start anywhere.
 __global__ void __launch_bounds__(VP_WARPS * 32)
-k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, const uint32_t* __restrict__ list, uint32_t* __restrict__ sym, const GatherGeom G) {
+k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, const uint32_t* __restrict__ list, uint32_t* __restrict__ sym, const GatherGeom G,
+           const uint32_t split) {
     extern __shared__ __align__(16) uint32_t s_log_raw[];     // [VP_WARPS][VP_WORDS + VP_MIRROR][32]
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const uint32_t g = blockIdx.x * VP_WARPS + w;
+    const uint32_t gw = blockIdx.x * VP_WARPS + w;
+    const uint32_t g = gw / split, part = gw - g * split;
     if (g >= plan->n_groups) return;
     uint32_t list0, n_in, row0;
     vl_locate(plan, g, list0, n_in, row0);
@@ -197,11 +204,22 @@ k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, 
         for (uint32_t k = 0; k + 1u < DABGPU_MAX_SEGMENTS; k++) odd = odd || ((J->seg_step_end[k] & 7u) != 0u && J->seg_step_end[k] < N);
     }
     const bool any_odd = __any_sync(FULL_MASK, odd);
-    uint32_t next_unit = have ? ((origin + S.inb) / VP_UNIT) : 0u;   // units below this one are in the window (the last two of them)
+    // this warp's tiles
+    const uint32_t n_tiles = (padded + VP_TILE - 1u) / VP_TILE, per_part = (n_tiles + split - 1u) / split;
+    const uint32_t t_begin = part * per_part * VP_TILE, t_end = min(padded, (part + 1u) * per_part * VP_TILE);
+    uint32_t next_unit = 0u;                 // units below this one are in the window (the last two of them)
+    if (have) {
+        if (t_begin < N) {
+            while (t_begin >= S.seg_end && S.seg < DABGPU_MAX_SEGMENTS - 1u) prep_seg_load(S, J, S.seg + 1u);
+            next_unit = (origin + prep_in_index(S, t_begin)) / VP_UNIT;
+        } else {
+            next_unit = 0xFFFFFFFFu;         // beyond the end of this trellis: zeros only, nothing to fetch
+        }
+    }
     uint32_t* __restrict__ dst = sym + size_t(row0) * 32u + lane;
 
 #pragma unroll 1
-    for (uint32_t t0 = 0; t0 < padded; t0 += VP_TILE) {
+    for (uint32_t t0 = t_begin; t0 < t_end; t0 += VP_TILE) {
         // ---- A. refill: the tile reads at most 4 * VP_TILE = 128 symbols from the position of its first step ----
         uint32_t need_unit = 0;
         if (t0 < N) {
