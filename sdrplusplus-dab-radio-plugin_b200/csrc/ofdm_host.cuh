@@ -18,6 +18,9 @@ struct OfdmState {
     int bps = 2;
     DevBuf d_diag, d_diag_meta, d_diag_fft, d_ring, d_st, d_null_ring, d_corr, d_head, d_phase, d_tw, d_prs_conj, d_prs_time, d_dpos, d_outpos, d_obin, d_stage, d_produced;
     int num_sms = 148;
+    // k_ofdm_demod2 CTAs per SM are capped (through the shared-memory request) while a channel decode runs on its own stream: its
+    // kernels then find room next to the demodulator instead of queueing behind a full wave of it (0 = no cap)
+    int demod_ctas_cap = 0;
     // second stream: the streams of a launch are split in two groups so that the latency-bound control kernel of one
     // group overlaps the demodulation kernel of the other
     cudaStream_t aux_stream = nullptr;
@@ -271,8 +274,15 @@ static int ofdm_reset(OfdmState& O, int stream, cudaStream_t cs) {
     return DABGPU_OK;
 }
 
+// At most n CTAs of k_ofdm_demod2 per SM (by asking for 1/n of the shared memory).  DABGPU_DEMOD_CTAS overrides (tuning knob).
+static int demod_smem_request(int need, int cap) {
+    if (const char* e = getenv("DABGPU_DEMOD_CTAS")) cap = atoi(e);
+    if (cap >= 1 && cap <= 8) return std::max(need, (227 * 1024) / cap - 2048);
+    return need;
+}
+
 template <int N, int FMT> static int demod_set_attr_t() {
-    CUDA_TRY(cudaFuncSetAttribute(k_ofdm_demod2<N, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(DemodCfg<N, FMT>::SMEM)));
+    CUDA_TRY(cudaFuncSetAttribute(k_ofdm_demod2<N, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(int(DemodCfg<N, FMT>::SMEM), 227 * 1024 - 2048)));
     return DABGPU_OK;
 }
 static int demod_set_attributes(int N, int fmt) {
@@ -320,7 +330,7 @@ static void ofdm_launch_group(OfdmState& O, int first, int n, int n_samples, int
         k_ofdm_ctl<N><<<n, N / 8, 0, cs>>>(O.dev, first, n_samples, block_size, it == 0 ? 1 : 0);
         pf.end(cs);
         pf.begin(PROF_OFDM_DEMOD, cs);
-        k_ofdm_demod2<N, FMT><<<dgrid, N / 8, DemodCfg<N, FMT>::SMEM, cs>>>(O.dev, first, spc);
+        k_ofdm_demod2<N, FMT><<<dgrid, N / 8, demod_smem_request(int(DemodCfg<N, FMT>::SMEM), (N == 2048 && n >= 128) ? O.demod_ctas_cap : 0), cs>>>(O.dev, first, spc);
         pf.end(cs);
         O.launches += 2;
     }
