@@ -114,32 +114,14 @@ __device__ int rs_solve(const GfTables& T, const uint8_t* S, int nroots, int pad
 
 #define DP_WARPS 4
 #define DP_SF_SMEM 1920   // superframes up to 128 kbit/s (5 x 384 bytes) are staged in shared memory per warp
-struct DpShared {
-    uint8_t gf_ex[512];
-    uint8_t gf_lg[256];
-    uint16_t crc_ccitt[256];
-    uint16_t crc_fire[256];
-    // branch-free x * alpha^r for the syndrome loop: gf_exz[gf_lgx[x] + r] with log(0) mapped past the end of the exp table
-    uint16_t gf_lgx[256];
-    uint8_t gf_exz[528];
-    // x -> x * alpha^r for the roots r = 2..9 of the DAB+ code: one lookup per Horner step (root 0 needs none, root 1 is a shift)
-    uint8_t gf_mulr[8][256];
+struct DpShared : DpTables {
     __align__(16) uint8_t sfbuf[DP_WARPS][DP_SF_SMEM];
 };
 
 __device__ __forceinline__ void dp_load_shared(DpShared& sh) {
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) sh.gf_ex[i] = c_gf_exp[i];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        sh.gf_lg[i] = c_gf_log[i];
-        sh.crc_ccitt[i] = c_crc_ccitt[i];
-        sh.crc_fire[i] = c_crc_fire[i];
-        sh.gf_lgx[i] = i ? uint16_t(c_gf_log[i]) : uint16_t(512);
-    }
-    for (int i = threadIdx.x; i < 528; i += blockDim.x) sh.gf_exz[i] = (i < 510) ? c_gf_exp[i] : uint8_t(0);
-    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) {
-        const int r = 2 + (i >> 8), x = i & 255;
-        sh.gf_mulr[i >> 8][x] = x ? c_gf_exp[c_gf_log[x] + r] : uint8_t(0);
-    }
+    const uint4* src = reinterpret_cast<const uint4*>(&g_dp_tables);
+    uint4* dst = reinterpret_cast<uint4*>(static_cast<DpTables*>(&sh));
+    for (int i = threadIdx.x; i < int(sizeof(DpTables) / 16); i += blockDim.x) dst[i] = src[i];
     __syncthreads();
 }
 
@@ -193,6 +175,25 @@ __device__ int dp_read_au_start(const uint8_t* buf, uint16_t* data, int n) {
         data[i] = uint16_t(v);
     }
     return (bitpos + 7) >> 3;
+}
+
+// n bytes by a warp: 8-byte words when the layout allows it (logical frames are multiples of 24 bytes at multiples of 8), all
+// loads of a lane issued before its stores
+__device__ __forceinline__ void dp_copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, const int n, const uint32_t lane) {
+    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | uintptr_t(n)) & 7u) == 0u) {
+        const uint2* s8 = reinterpret_cast<const uint2*>(src);
+        uint2* d8 = reinterpret_cast<uint2*>(dst);
+        const int n8 = n >> 3;
+        for (int i0 = 0; i0 < n8; i0 += 128) {
+            uint2 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int i = i0 + int(lane) + 32 * k; if (i < n8) v[k] = s8[i]; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int i = i0 + int(lane) + 32 * k; if (i < n8) d8[i] = v[k]; }
+        }
+    } else {
+        for (int i = int(lane); i < n; i += 32) dst[i] = src[i];
+    }
 }
 
 // ProcessSuperFrame for one sub-channel, executed by a full warp.  Returns nothing; state/event side effects.
@@ -292,7 +293,7 @@ __device__ void dp_superframe(DpShared& sh, uint8_t* sf_global, uint8_t* sf_out,
     ok = __shfl_sync(FULL_MASK, ok, 0);
     if (!ok) return;
     // the accumulator is reused by the following CIFs of this frame: keep the validated superframe for the host
-    for (int i = int(lane); i < total; i += 32) sf_out[i] = sf[i];
+    dp_copy_bytes(sf_out, sf, total, lane);
     // header (aac_frame_processor.cpp:215-279)
     const uint8_t dsc = sf[2];
     const int dac_rate = (dsc >> 6) & 1, sbr = (dsc >> 5) & 1, ch = (dsc >> 4) & 1, ps = (dsc >> 3) & 1, mpeg = dsc & 7;
@@ -350,7 +351,7 @@ __device__ void dp_process_frame(DpShared& sh, const uint8_t* __restrict__ buf, 
         if (!ok) return;
         st.collect = 1;
     }
-    for (int i = int(lane); i < n; i += 32) sf[size_t(st.curr_frame) * n + i] = buf[i];
+    dp_copy_bytes(sf + size_t(st.curr_frame) * n, buf, n, lane);
     __syncwarp();
     st.curr_frame++;
     if (st.curr_frame == 5) {

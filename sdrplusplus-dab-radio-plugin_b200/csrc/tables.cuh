@@ -47,6 +47,23 @@ __constant__ uint8_t c_ti_age[16];
 __constant__ uint8_t c_gf_exp[512];
 __constant__ uint8_t c_gf_log[256];
 
+// The lookup tables k_dabplus / k_rs_batch / k_packet_fec keep in shared memory, built once on the host and copied by every CTA
+// with 16-byte loads (reading the __constant__ tables above with a different index per lane serialises in the constant cache:
+// 23 % of k_dabplus's stall samples went there).
+struct DpTables {
+    uint8_t gf_ex[512];
+    uint8_t gf_lg[256];
+    uint16_t crc_ccitt[256];
+    uint16_t crc_fire[256];
+    // branch-free x * alpha^r: gf_exz[gf_lgx[x] + r] with log(0) mapped past the end of the exp table
+    uint16_t gf_lgx[256];
+    uint8_t gf_exz[528];
+    // x -> x * alpha^r for the roots r = 2..9 of the DAB+ code: one lookup per Horner step (root 0 needs none, root 1 is a shift)
+    uint8_t gf_mulr[8][256];
+};
+static_assert(sizeof(DpTables) % 16 == 0, "copied in 16-byte pieces");
+__device__ __align__(16) DpTables g_dp_tables;
+
 static int upload_constant_tables() {
     uint32_t cnt[25], K[25];
     uint64_t pref[25];
@@ -124,6 +141,18 @@ static int upload_constant_tables() {
     ex[255] = ex[0];
     CUDA_TRY(cudaMemcpyToSymbol(c_gf_exp, ex, sizeof(ex)));
     CUDA_TRY(cudaMemcpyToSymbol(c_gf_log, lg, sizeof(lg)));
+    {
+        static DpTables T;
+        memcpy(T.gf_ex, ex, sizeof(ex));
+        memcpy(T.gf_lg, lg, sizeof(lg));
+        memcpy(T.crc_ccitt, t1, sizeof(t1));
+        memcpy(T.crc_fire, t2, sizeof(t2));
+        for (int i = 0; i < 256; i++) T.gf_lgx[i] = i ? uint16_t(lg[i]) : uint16_t(512);
+        for (int i = 0; i < 528; i++) T.gf_exz[i] = (i < 510) ? ex[i] : uint8_t(0);
+        for (int r = 2; r < 10; r++)
+            for (int x = 0; x < 256; x++) T.gf_mulr[r - 2][x] = x ? ex[lg[x] + r] : uint8_t(0);
+        CUDA_TRY(cudaMemcpyToSymbol(g_dp_tables, &T, sizeof(T)));
+    }
     return DABGPU_OK;
 }
 
