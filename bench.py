@@ -352,7 +352,12 @@ def main():
     subs = tx.default_ensemble()
     # two distinct periodic coded ensembles (FIC + 18 x EEP 3-A DAB+ sub-channels), shared by the streams with different channels
     payload = np.stack([tx.periodic_frames(1, subs, seed=1000 * (rank + 1) + u, period_frames=PERIOD_FRAMES) for u in range(2)])
-    cyc, _, _ = synth.make_cyclic_streams_u8(S, payload, mode=1, seed0=1 + rank, snr_db=15.0, device=str(dev))
+    # the job is world * S streams; stream s belongs to rank s mod world (shard.py) -- no data-path collective, every rank builds
+    # and decodes only its own streams (the channel of a stream is seeded by the first global id of the rank's share)
+    shard = importlib.import_module(PKG + ".shard")
+    my_streams = shard.streams_for_rank(world * S, rank, world)
+    assert len(my_streams) == S and all(shard.owner_of(s_, world) == rank for s_ in my_streams)
+    cyc, _, _ = synth.make_cyclic_streams_u8(S, payload, mode=1, seed0=1 + my_streams[0], snr_db=15.0, device=str(dev))
     n_frames = W + 2 * K + 2          # K timed steps for `value`, K more with per-kernel CUDA events for the roofline
     reps = (n_frames + PERIOD_FRAMES - 1) // PERIOD_FRAMES
     iq = cyc.repeat(1, reps)

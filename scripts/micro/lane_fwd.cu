@@ -26,12 +26,12 @@ __global__ void __launch_bounds__(512, 1) k(const uint32_t* __restrict__ sym, ui
         if (V == 0) vl_step5(S, w, g * 5, GROUPS * 5, dd, frel, kc);
         else {
             uint32_t Ea[8], Eia[8], Eb[8], Eib[8];
-            vl_branch<0>(w[0], Ea, Eia, kc);
-            vl_acs<0>(S.R, Ea, Eia, S.CL, dd[0], dd[1], kc); vl_branch<1>(w[1], Eb, Eib, kc);
-            vl_acs<1>(S.R, Eb, Eib, S.CL, dd[2], dd[3], kc); vl_branch<2>(w[2], Ea, Eia, kc);
-            vl_acs<2>(S.R, Ea, Eia, S.CL, dd[4], dd[5], kc); vl_branch<3>(w[3], Eb, Eib, kc);
-            vl_acs<3>(S.R, Eb, Eib, S.CL, dd[6], dd[7], kc); vl_branch<4>(w[4], Ea, Eia, kc);
-            vl_acs<4>(S.R, Ea, Eia, S.CL, dd[8], dd[9], kc);
+            vl_branch<0, true>(w[0], Ea, Eia, kc);
+            vl_acs<0, true>(S.R, Ea, Eia, S.CL, dd[0], dd[1], kc); vl_branch<1, true>(w[1], Eb, Eib, kc);
+            vl_acs<1, true>(S.R, Eb, Eib, S.CL, dd[2], dd[3], kc); vl_branch<2, true>(w[2], Ea, Eia, kc);
+            vl_acs<2, true>(S.R, Ea, Eia, S.CL, dd[4], dd[5], kc); vl_branch<3, true>(w[3], Eb, Eib, kc);
+            vl_acs<3, true>(S.R, Eb, Eib, S.CL, dd[6], dd[7], kc); vl_branch<4, true>(w[4], Ea, Eia, kc);
+            vl_acs<4, true>(S.R, Ea, Eia, S.CL, dd[8], dd[9], kc);
             vl_repack(S.R);
             if (V == 1) {
                 const uint32_t delta = (S.R[0] & 0xFFFFu) - VL_ORIGIN;

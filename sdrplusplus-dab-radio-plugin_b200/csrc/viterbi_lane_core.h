@@ -129,20 +129,27 @@ VL_HD void vl_reset(VlState& S) {
 // Branch errors of one trellis step, paired for layout K.  w = the four soft symbols of the step (int8 each, punctured = 0).
 // E[p] = (e[p], e[p ^ dK]) and Ei[p] = (1016 - e, clamped at 0) for the two butterflies that share a register.
 // Independent of the path metrics: vl_step5 issues it one step ahead so that it overlaps the tail of the previous step.
-template <int K>
+//
+// M128 = false: the caller guarantees that no symbol of the call is -128 (true for everything the OFDM stage produces; the
+// de-puncture pass looks).  Then |b - w| + |-b - w| = 254 for b = +-127, so the error of the complementary pattern is exactly
+// the inverse error, 1016 - e[p] = e[p ^ 7] with no clamp to apply: Ei[p] = E[p ^ 7], and the eight subtractions, eight clamps
+// and eight pairings of the general form (24 of 264 instructions per step) are not needed.  Ei is left untouched.
+template <int K, bool M128>
 VL_HD void vl_branch(const uint32_t w, uint32_t (&E)[8], uint32_t (&Ei)[8], const VlConst kc) {
     uint32_t e[8], ei[8];
 #pragma unroll
     for (int p = 0; p < 8; p++) {
         e[p] = vl_absdiff4(vl_bt(uint32_t(p)), w);
-        const int32_t inv = int32_t(vl_mad(e[p], kc.m1, VL_MAX_ERROR));   // 1016 - e
-        ei[p] = uint32_t(inv < 0 ? 0 : inv);
+        if (M128) {
+            const int32_t inv = int32_t(vl_mad(e[p], kc.m1, VL_MAX_ERROR));   // 1016 - e
+            ei[p] = uint32_t(inv < 0 ? 0 : inv);
+        }
     }
     constexpr uint32_t dk = vl_pat(1u << K);   // pattern difference between the two butterflies sharing a register
 #pragma unroll
     for (int p = 0; p < 8; p++) {
         E[p] = vl_mad(e[uint32_t(p) ^ dk], kc.x10000, e[p]);
-        Ei[p] = vl_mad(ei[uint32_t(p) ^ dk], kc.x10000, ei[p]);
+        if (M128) Ei[p] = vl_mad(ei[uint32_t(p) ^ dk], kc.x10000, ei[p]);
     }
 }
 
@@ -161,18 +168,19 @@ VL_HD uint32_t vl_gather16(const uint32_t (&z)[16], const VlConst kc) {
 // One trellis step from layout K to layout K+1 (add-compare-select of the 32 butterflies).
 // d0/d1 receive the decision bits of the even/odd new states: new state n = 2j + (n & 1), i = j with bit K removed,
 // position i + 16 * (bit K of j).
-template <int K>
+template <int K, bool M128>
 VL_HD void vl_acs(uint32_t (&R)[32], const uint32_t (&E)[8], const uint32_t (&Ei)[8], const uint32_t CL, uint32_t& d0, uint32_t& d1, const VlConst kc) {
     uint32_t Rn[32], z0[16], z1[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const uint32_t p = vl_pat(vl_insert0(uint32_t(i), uint32_t(K)));
         const uint32_t M0 = R[i], M1 = R[i + 16];
-        const uint32_t B = vl_addmin(M1, Ei[p], CL);       // upper predecessor, saturating like the reference
-        const uint32_t N0 = vl_addmin(M0, E[p], B);        // new[2j]
+        const uint32_t ep = E[p], eip = M128 ? Ei[p] : E[p ^ 7u];
+        const uint32_t B = vl_addmin(M1, eip, CL);         // upper predecessor, saturating like the reference
+        const uint32_t N0 = vl_addmin(M0, ep, B);          // new[2j]
         z0[i] = vl_min(vl_mad(N0, kc.m1, B), 0x00010001u);   // 0 where the upper path won or tied
-        const uint32_t D = vl_addmin(M1, E[p], CL);
-        const uint32_t N1 = vl_addmin(M0, Ei[p], D);       // new[2j+1]
+        const uint32_t D = vl_addmin(M1, ep, CL);
+        const uint32_t N1 = vl_addmin(M0, eip, D);         // new[2j+1]
         z1[i] = vl_min(vl_mad(N1, kc.m1, D), 0x00010001u);
         Rn[2 * i] = N0;
         Rn[2 * i + 1] = N1;
@@ -225,16 +233,20 @@ VL_HD uint64_t vl_final_error(const VlState& S, const uint32_t final_rel) { retu
 
 // Five trellis steps t0 .. t0+4 starting and ending in layout 0.  emit(k, d0, d1) receives the decision words of step t0+k as
 // soon as they exist (the kernel stores them at once: ten live registers less than keeping them to the end of the iteration).
-template <class Emit>
+template <bool M128, class Emit>
 VL_HD void vl_step5_emit(VlState& S, const uint32_t (&w)[VL_UNROLL], const uint32_t t0, const uint32_t n_steps, Emit&& emit, uint32_t& final_rel,
                          const VlConst kc) {
     uint32_t Ea[8], Eia[8], Eb[8], Eib[8], d0, d1;
-    vl_branch<0>(w[0], Ea, Eia, kc);
-    vl_acs<0>(S.R, Ea, Eia, S.CL, d0, d1, kc); emit(0, d0, d1); vl_branch<1>(w[1], Eb, Eib, kc); vl_after_step(S, t0 + 0u, n_steps, final_rel);
-    vl_acs<1>(S.R, Eb, Eib, S.CL, d0, d1, kc); emit(1, d0, d1); vl_branch<2>(w[2], Ea, Eia, kc); vl_after_step(S, t0 + 1u, n_steps, final_rel);
-    vl_acs<2>(S.R, Ea, Eia, S.CL, d0, d1, kc); emit(2, d0, d1); vl_branch<3>(w[3], Eb, Eib, kc); vl_after_step(S, t0 + 2u, n_steps, final_rel);
-    vl_acs<3>(S.R, Eb, Eib, S.CL, d0, d1, kc); emit(3, d0, d1); vl_branch<4>(w[4], Ea, Eia, kc); vl_after_step(S, t0 + 3u, n_steps, final_rel);
-    vl_acs<4>(S.R, Ea, Eia, S.CL, d0, d1, kc); emit(4, d0, d1); vl_after_step(S, t0 + 4u, n_steps, final_rel);
+    if (!M128) {
+#pragma unroll
+        for (int p = 0; p < 8; p++) { Eia[p] = 0u; Eib[p] = 0u; }    // never read
+    }
+    vl_branch<0, M128>(w[0], Ea, Eia, kc);
+    vl_acs<0, M128>(S.R, Ea, Eia, S.CL, d0, d1, kc); emit(0, d0, d1); vl_branch<1, M128>(w[1], Eb, Eib, kc); vl_after_step(S, t0 + 0u, n_steps, final_rel);
+    vl_acs<1, M128>(S.R, Eb, Eib, S.CL, d0, d1, kc); emit(1, d0, d1); vl_branch<2, M128>(w[2], Ea, Eia, kc); vl_after_step(S, t0 + 1u, n_steps, final_rel);
+    vl_acs<2, M128>(S.R, Ea, Eia, S.CL, d0, d1, kc); emit(2, d0, d1); vl_branch<3, M128>(w[3], Eb, Eib, kc); vl_after_step(S, t0 + 2u, n_steps, final_rel);
+    vl_acs<3, M128>(S.R, Eb, Eib, S.CL, d0, d1, kc); emit(3, d0, d1); vl_branch<4, M128>(w[4], Ea, Eia, kc); vl_after_step(S, t0 + 3u, n_steps, final_rel);
+    vl_acs<4, M128>(S.R, Ea, Eia, S.CL, d0, d1, kc); emit(4, d0, d1); vl_after_step(S, t0 + 4u, n_steps, final_rel);
     vl_repack(S.R);
     // own renormalisation: bring rel[0] back to VL_ORIGIN (delta >= 0: metrics never decrease)
     const uint32_t delta = (S.R[0] & 0xFFFFu) - VL_ORIGIN;
@@ -245,9 +257,16 @@ VL_HD void vl_step5_emit(VlState& S, const uint32_t (&w)[VL_UNROLL], const uint3
 }
 
 // the same with the decision words returned: dec[2k], dec[2k+1] = step t0+k
+template <bool M128 = true>
 VL_HD void vl_step5(VlState& S, const uint32_t (&w)[VL_UNROLL], const uint32_t t0, const uint32_t n_steps, uint32_t (&dec)[2 * VL_UNROLL],
                     uint32_t& final_rel, const VlConst kc) {
-    vl_step5_emit(S, w, t0, n_steps, [&](const int k, const uint32_t d0, const uint32_t d1) { dec[2 * k] = d0; dec[2 * k + 1] = d1; }, final_rel, kc);
+    vl_step5_emit<M128>(S, w, t0, n_steps, [&](const int k, const uint32_t d0, const uint32_t d1) { dec[2 * k] = d0; dec[2 * k + 1] = d1; }, final_rel, kc);
+}
+
+// true if one of the four int8 symbols of a word is -128 (the exact-zero-byte test on w ^ 0x80808080)
+VL_HD bool vl_has_m128(const uint32_t w) {
+    const uint32_t t = w ^ 0x80808080u;
+    return ((t - 0x01010101u) & ~t & 0x80808080u) != 0u;
 }
 
 // Traceback: the decision bit of new state n at a step whose index is k modulo 5.

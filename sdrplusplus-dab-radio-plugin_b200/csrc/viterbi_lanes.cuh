@@ -29,7 +29,8 @@ __host__ __device__ inline uint32_t vl_bucket_rows(uint32_t b) { return vl_bucke
 struct VlPlan {
     uint32_t use_lanes, n_groups, n_active, oversize;
     uint32_t next_group;              // work counter of k_viterbi_lanes
-    uint32_t pad_[3];
+    uint32_t has_m128;                // k_vit_prep found a -128 symbol in the call: the decoder takes the general branch-error form
+    uint32_t pad_[2];
     uint32_t count[VL_BUCKETS];       // trellises per class
     uint32_t cursor[VL_BUCKETS];      // scatter cursors
     uint32_t list_base[VL_BUCKETS];   // first entry of the class in the job list
@@ -167,7 +168,7 @@ __device__ __forceinline__ uint32_t prep_word(const uint32_t (*L)[32], const uin
 // dependent refill -> de-puncture -> store chain, and a call has only as many groups as a quarter of the warps the GPU can
 // hold; the step -> input index map (prep_in_index) is random access, so the walk can start anywhere.
 __global__ void __launch_bounds__(VP_WARPS * 32)
-k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, const uint32_t* __restrict__ list, uint32_t* __restrict__ sym, const GatherGeom G,
+k_vit_prep(const VitJobDev* __restrict__ jobs, VlPlan* __restrict__ plan, const uint32_t* __restrict__ list, uint32_t* __restrict__ sym, const GatherGeom G,
            const uint32_t split) {
     extern __shared__ __align__(16) uint32_t s_log_raw[];     // [VP_WARPS][VP_WORDS + VP_MIRROR][32]
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
@@ -217,6 +218,7 @@ k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, 
         }
     }
     uint32_t* __restrict__ dst = sym + size_t(row0) * 32u + lane;
+    bool m128 = false;                       // a -128 symbol went by (vl_branch: the decoder's short form needs |symbol| <= 127)
 
 #pragma unroll 1
     for (uint32_t t0 = t_begin; t0 < t_end; t0 += VP_TILE) {
@@ -256,6 +258,7 @@ k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, 
                     const uint32_t g8 = (t - S.start) & 7u;
                     word = prep_word(L, lane, origin + prep_in_index(S, t), (S.cntw >> (4u * g8)) & 0xFu);
                 }
+                m128 = m128 || vl_has_m128(word);
                 dst[size_t(t) * 32u] = word;
             }
             __syncwarp();
@@ -298,11 +301,14 @@ k_vit_prep(const VitJobDev* __restrict__ jobs, const VlPlan* __restrict__ plan, 
                 }
             }
 #pragma unroll
-            for (uint32_t g8 = 0; g8 < 8u; g8++)
+            for (uint32_t g8 = 0; g8 < 8u; g8++) {
+                m128 = m128 || vl_has_m128(words[g8]);
                 if (tp + g8 < padded) dst[size_t(tp + g8) * 32u] = words[g8];
+            }
         }
         __syncwarp();
     }
+    if (__any_sync(FULL_MASK, m128) && lane == 0u) atomicOr(&plan->has_m128, 1u);
 }
 
 __device__ __forceinline__ void vl_emit_word(uint8_t* __restrict__ out, const uint32_t n_out_bytes, const uint32_t widx, const uint32_t v) {
@@ -396,6 +402,29 @@ __device__ __forceinline__ void vl_traceback(const uint2* __restrict__ dec, cons
 
 #define VL_WARPS_PER_BLOCK 4
 
+// Forward pass of one group.  M128: the general branch-error form (a -128 symbol somewhere in the call); otherwise the short one.
+template <bool M128>
+__device__ __forceinline__ void vl_forward(const uint32_t* __restrict__ srow, uint2* __restrict__ dec, const uint32_t padded, const uint32_t N,
+                                           unsigned long long* __restrict__ path_error, const VlConst kc) {
+    VlState S;
+    vl_reset(S);
+    uint32_t final_rel = 0;
+    uint32_t w[VL_UNROLL];
+#pragma unroll
+    for (int k = 0; k < VL_UNROLL; k++) w[k] = __ldg(srow + size_t(k) * 32u);
+#pragma unroll 1
+    for (uint32_t t0 = 0; t0 < padded; t0 += VL_UNROLL) {
+        uint32_t wn[VL_UNROLL];
+#pragma unroll
+        for (int k = 0; k < VL_UNROLL; k++) wn[k] = __ldg(srow + size_t(t0 + VL_UNROLL + k) * 32u);
+        uint2* __restrict__ drow = dec + size_t(t0) * 32u;
+        vl_step5_emit<M128>(S, w, t0, N, [&](const int k, const uint32_t d0, const uint32_t d1) { drow[k * 32] = make_uint2(d0, d1); }, final_rel, kc);
+#pragma unroll
+        for (int k = 0; k < VL_UNROLL; k++) w[k] = wn[k];
+    }
+    if (path_error != nullptr) *path_error = vl_final_error(S, final_rel);
+}
+
 // Two builds of the same kernel.  <40, 1>: one CTA per SM = one decoder warp per SM sub-partition, for calls with up to one
 // group per warp (256 streams x 76 trellises = 608 groups on 592 warps); the lone warp hides the latency of its traceback
 // loads with 2 x 40 rows in flight (240 registers).  <10, 4>: 128 registers, four CTAs per SM, for larger calls: a single
@@ -408,6 +437,7 @@ k_viterbi_lanes(const VitJobDev* __restrict__ jobs, VlPlan* __restrict__ plan, c
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t slot = blockIdx.x * VL_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     uint2* __restrict__ dec = scratch + size_t(slot) * scratch_rows * 32u + lane;
+    const bool m128 = plan->has_m128 != 0u;      // set by k_vit_prep, which has finished
     for (;;) {
         uint32_t g = 0;
         if (lane == 0) g = atomicAdd(&plan->next_group, 1u);
@@ -426,25 +456,8 @@ k_viterbi_lanes(const VitJobDev* __restrict__ jobs, VlPlan* __restrict__ plan, c
         const uint32_t* __restrict__ srow = sym + size_t(row0) * 32u + lane;
 
         // ---- forward pass: five trellis steps per iteration, symbols prefetched one iteration ahead ----
-        {
-            VlState S;
-            vl_reset(S);
-            uint32_t final_rel = 0;
-            uint32_t w[VL_UNROLL];
-#pragma unroll
-            for (int k = 0; k < VL_UNROLL; k++) w[k] = __ldg(srow + size_t(k) * 32u);
-#pragma unroll 1
-            for (uint32_t t0 = 0; t0 < padded; t0 += VL_UNROLL) {
-                uint32_t wn[VL_UNROLL];
-#pragma unroll
-                for (int k = 0; k < VL_UNROLL; k++) wn[k] = __ldg(srow + size_t(t0 + VL_UNROLL + k) * 32u);
-                uint2* __restrict__ drow = dec + size_t(t0) * 32u;
-                vl_step5_emit(S, w, t0, N, [&](const int k, const uint32_t d0, const uint32_t d1) { drow[k * 32] = make_uint2(d0, d1); }, final_rel, kc);
-#pragma unroll
-                for (int k = 0; k < VL_UNROLL; k++) w[k] = wn[k];
-            }
-            if (have && J->path_error != nullptr) *J->path_error = vl_final_error(S, final_rel);
-        }
+        if (m128) vl_forward<true>(srow, dec, padded, N, have ? J->path_error : nullptr, kc);
+        else vl_forward<false>(srow, dec, padded, N, have ? J->path_error : nullptr, kc);
 
         vl_traceback<TB>(dec, J, have, n_out_bytes, flags, out, prbs_words);
         __syncwarp();

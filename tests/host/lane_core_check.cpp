@@ -14,7 +14,8 @@
 static const VlConst KC = {0xFFFFFFFFu, 2u, 4u, 16u, 256u, 0x10000u};
 
 // returns the number of own-clamp activations seen (to prove that the saturating cases are exercised)
-static void lane_decode(const int8_t* soft4, uint32_t n_steps, uint8_t* out, uint32_t n_out_bytes, uint64_t* err, bool no_clamp) {
+// general = the branch-error form that tolerates -128 symbols (vl_branch<K, true>); the short form needs |symbol| <= 127
+static void lane_decode(const int8_t* soft4, uint32_t n_steps, uint8_t* out, uint32_t n_out_bytes, uint64_t* err, bool no_clamp, bool general = true) {
     VlState S;
     vl_reset(S);
     const uint32_t padded = ((n_steps + VL_UNROLL - 1) / VL_UNROLL) * VL_UNROLL;
@@ -27,7 +28,8 @@ static void lane_decode(const int8_t* soft4, uint32_t n_steps, uint8_t* out, uin
             if (t0 + k < n_steps) memcpy(&w[k], soft4 + 4 * size_t(t0 + k), 4);
         }
         if (no_clamp) S.CL = 0x7FFF7FFFu;
-        vl_step5(S, w, t0, n_steps, dec, final_rel, KC);
+        if (general) vl_step5<true>(S, w, t0, n_steps, dec, final_rel, KC);
+        else vl_step5<false>(S, w, t0, n_steps, dec, final_rel, KC);
         for (uint32_t k = 0; k < VL_UNROLL; k++) { d0[t0 + k] = dec[2 * k]; d1[t0 + k] = dec[2 * k + 1]; }
     }
     *err = vl_final_error(S, final_rel);
@@ -65,7 +67,7 @@ static void encode(const std::vector<uint8_t>& bits, std::vector<int8_t>& sym) {
 int main(int argc, char** argv) {
     const int trials = argc > 1 ? atoi(argv[1]) : 400;
     std::mt19937 rng(12345);
-    int bad = 0, clamp_mattered = 0;
+    int bad = 0, clamp_mattered = 0, short_form = 0;
     static const uint32_t lengths[] = {774, 1542, 6, 7, 14, 46, 262, 3078, 6150, 102};
     for (int trial = 0; trial < trials; trial++) {
         const uint32_t n_steps = lengths[trial % 10];
@@ -101,12 +103,29 @@ int main(int argc, char** argv) {
         lane_decode(soft.data(), n_steps, got.data(), n_out, &got_err, false);
         lane_decode(soft.data(), n_steps, got_nc.data(), n_out, &nc_err, true);
         if (memcmp(got_nc.data(), got.data(), n_out) != 0 || nc_err != got_err) clamp_mattered++;
+        // the short branch-error form, where it applies (no -128 anywhere; the kernel decides per call with vl_has_m128)
+        bool m128 = false;
+        for (size_t i = 0; i + 3 < soft.size(); i += 4) { uint32_t wv; memcpy(&wv, &soft[i], 4); m128 = m128 || vl_has_m128(wv); }
+        bool truth = false;
+        for (size_t i = 0; i < soft.size(); i++) truth = truth || soft[i] == -128;
+        if (truth != m128) { printf("vl_has_m128 wrong in trial %d\n", trial); bad++; }
+        if (!m128) {
+            short_form++;
+            std::vector<uint8_t> got_s(n_out + 1);
+            uint64_t s_err = 0;
+            lane_decode(soft.data(), n_steps, got_s.data(), n_out, &s_err, false, false);
+            if (memcmp(exp.data(), got_s.data(), n_out) != 0 || exp_err != s_err) {
+                bad++;
+                if (bad <= 10) printf("MISMATCH (short form) trial %d kind %d steps %u\n", trial, kind, n_steps);
+            }
+        }
         if (memcmp(exp.data(), got.data(), n_out) != 0 || exp_err != got_err) {
             bad++;
             if (bad <= 10) printf("MISMATCH trial %d kind %d steps %u: err oracle %llu lane %llu\n", trial, kind, n_steps,
                                   (unsigned long long)exp_err, (unsigned long long)got_err);
         }
     }
-    printf("lane_core_check: %d trials, %d mismatches, saturation clamp changed the result in %d trials\n", trials, bad, clamp_mattered);
+    printf("lane_core_check: %d trials, %d mismatches, saturation clamp changed the result in %d trials, short branch-error form checked in %d\n", trials, bad,
+           clamp_mattered, short_form);
     return bad ? 1 : 0;
 }
