@@ -63,6 +63,7 @@ VL_HD uint32_t vl_mad(uint32_t a, uint32_t b, uint32_t c) {
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+VL_HD uint32_t vl_dot4(uint32_t a, uint32_t b, uint32_t c) { return uint32_t(__dp4a(int(a), int(b), int(c))); }   // c + sum of int8 products (IDP4A, FMA pipe)
 #else
 VL_HD uint32_t vl_min(uint32_t a, uint32_t b) {
     const uint32_t al = a & 0xFFFFu, bl = b & 0xFFFFu, ah = a >> 16, bh = b >> 16;
@@ -87,6 +88,11 @@ VL_HD uint32_t vl_absdiff4(uint32_t bt, uint32_t w) {
     return e;
 }
 VL_HD uint32_t vl_mad(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+VL_HD uint32_t vl_dot4(uint32_t a, uint32_t b, uint32_t c) {
+    int32_t acc = int32_t(c);
+    for (int r = 0; r < 4; r++) acc += int32_t(int8_t(a >> (8 * r))) * int32_t(int8_t(b >> (8 * r)));
+    return uint32_t(acc);
+}
 #endif
 
 // ---- compile-time geometry ------------------------------------------------------------------------------------------
@@ -99,6 +105,11 @@ VL_HD constexpr uint32_t vl_pat(uint32_t j) {
 // the four expected outputs (+127 / -127 as int8) of pattern p, packed like the received symbol word
 VL_HD constexpr uint32_t vl_bt(uint32_t p) {
     return ((p & 1u) ? 0x7Fu : 0x81u) | (((p & 2u) ? 0x7Fu : 0x81u) << 8) | (((p & 4u) ? 0x7Fu : 0x81u) << 16) | (((p & 1u) ? 0x7Fu : 0x81u) << 24);
+}
+// minus the signs of pattern p's expected symbols, one int8 each: for |w| <= 127 the branch error is
+// sum |(+-127) - w| = 508 - sum sign * w = 508 + dot(vl_negsign(p), w)
+VL_HD constexpr uint32_t vl_negsign(uint32_t p) {
+    return ((p & 1u) ? 0xFFu : 0x01u) | (((p & 2u) ? 0xFFu : 0x01u) << 8) | (((p & 4u) ? 0xFFu : 0x01u) << 16) | (((p & 1u) ? 0xFFu : 0x01u) << 24);
 }
 VL_HD constexpr uint32_t vl_insert0(uint32_t i, uint32_t k) { return ((i >> k) << (k + 1u)) | (i & ((1u << k) - 1u)); }
 
@@ -139,7 +150,8 @@ VL_HD void vl_branch(const uint32_t w, uint32_t (&E)[8], uint32_t (&Ei)[8], cons
     uint32_t e[8], ei[8];
 #pragma unroll
     for (int p = 0; p < 8; p++) {
-        e[p] = vl_absdiff4(vl_bt(uint32_t(p)), w);
+        // short form: the error as a dot product (FMA pipe; VABSDIFF4 shares the ALU pipe with the add-compare-select)
+        e[p] = M128 ? vl_absdiff4(vl_bt(uint32_t(p)), w) : vl_dot4(w, vl_negsign(uint32_t(p)), 508u);
         if (M128) {
             const int32_t inv = int32_t(vl_mad(e[p], kc.m1, VL_MAX_ERROR));   // 1016 - e
             ei[p] = uint32_t(inv < 0 ? 0 : inv);
