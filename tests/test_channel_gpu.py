@@ -5,6 +5,8 @@ Bar: bit-exact decoded bytes, path errors, CRC flags, RS corrections and superfr
 import numpy as np
 import pytest
 
+from conftest import VIT_LANES_ALWAYS
+
 pytestmark = pytest.mark.gpu
 
 
@@ -48,6 +50,30 @@ def test_viterbi_matches_oracles(gpu_ctx, tx, pyref, vit_flags):
             r, _, r_err = ref.decode(soft, sg)
             assert np.array_equal(outs[i], r), f"trellis {i}: bytes differ from the reference build"
             assert int(perr[i]) == r_err
+    g.close()
+
+
+def test_viterbi_lane_short_and_general_branch_error_forms(gpu_ctx, tx, pyref):
+    """k_viterbi_lanes takes the short branch-error form (Ei[p] = E[p ^ 7], dot-product errors) when k_vit_prep saw no -128 symbol
+    in the call and the general one otherwise (viterbi_lane_core.h: vl_branch).  A call without any -128 -- noiseless, noisy, tie
+    heavy and full-range garbage clipped at -127 -- must equal the oracle; the same call with ONE symbol set to -128 switches the
+    whole call to the general form and must equal the oracle again, bytes and path errors."""
+    rng = np.random.default_rng(21)
+    softs, segs = _mk_trellis_cases(tx, rng, 120)
+    softs = [np.maximum(s, -127).astype(np.int8) for s in softs]
+    assert all(int(s.min()) >= -127 for s in softs)
+    port = pyref.PortViterbi()
+    ref = pyref.RefViterbi() if pyref.ref_available() else None
+    g = gpu_ctx.DabGpu(mode=1, max_streams=1, flags=VIT_LANES_ALWAYS)
+    for variant in ("short", "general"):
+        if variant == "general":
+            softs[37] = softs[37].copy()
+            softs[37][softs[37].size // 2] = -128
+        outs, perr = g.viterbi_decode(softs, segs)
+        for i, (soft, sg) in enumerate(zip(softs, segs)):
+            exp, _, exp_err = (ref or port).decode(soft, sg)
+            assert np.array_equal(outs[i], exp), f"{variant} form, trellis {i}: bytes differ"
+            assert int(perr[i]) == exp_err, f"{variant} form, trellis {i}: path error {int(perr[i])} != {exp_err}"
     g.close()
 
 
