@@ -463,6 +463,11 @@ static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, 
             // demodulator capped at two as well, so that the two kernels always share every SM half and half (2.52 ms per
             // 1024-stream step against 2.58 for three + three and 2.87 run one after the other; profiles/r2_coresidency_*.txt)
             int per_sm = ctx->ofdm_since_chan ? 2 : 3;
+            // a call with slightly more groups than warps would run a second, nearly empty wave of whole trellises: one CTA more
+            {
+                const uint32_t slots = uint32_t(ctx->num_sms) * VL_WARPS_PER_BLOCK * uint32_t(per_sm);
+                if (groups > slots && groups * 4u < slots * 5u) per_sm++;
+            }
             if (const char* e = getenv("DABGPU_LANES_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 4) per_sm = v; }   // tuning knob
             k_viterbi_lanes<10u, 4><<<ctx->num_sms * per_sm, VL_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(), ctx->d_vlsym.as<uint32_t>(),
                                                                                                 ctx->d_vlscratch.as<uint2>(), ctx->vl_scratch_rows,

@@ -307,7 +307,9 @@ k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) 
                 if (k > 0) v = cmul_tw(v, D.tw, r * k * (N / 512));
                 sA[DEMOD_PADA(base + k * 64)] = v;
             }
-            __syncthreads();   // (2)
+            // (2) a block of 512 points belongs to the 64 threads with the same q, in this pass and in the next one: only those
+            // two warps meet (named barrier 1 + q), not the CTA
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
         }
         // ---- radix-8 pass over blocks of 64: A -> B (layout L3) ----------------------------------------
         {
@@ -324,7 +326,9 @@ k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) 
                 sB[DEMOD_L3(base + k * 8)] = v;
             }
         }
-        __syncthreads();   // (3)
+        // (3) a block of 64 points is written by eight consecutive threads and its eight contiguous runs are read back by the same
+        // eight: sB is private to the warp
+        __syncwarp();
         // ---- last radix-8 pass: 8 contiguous points, spectrum stays in registers -----------------------
         {
             const float4* p = reinterpret_cast<const float4*>(sB + (10 * tid + ((tid >> 3) << 3)));
