@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(N / 8, (N == 2048) ? 4 : (N == 1024 ? 6 : 8))
 k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) {
     using C = DemodCfg<N, FMT>;
     constexpr int T = C::T, CP = C::CP, TSYM = C::TSYM, K = C::K, BPS = C::BPS;
+    // the per-symbol single-thread chores go to different warps, so that no warp is late for the CTA barriers by both of them
+    constexpr int T_PREFETCH = (T > 32) ? 32 : 0, T_PHASE = (T > 64) ? 64 : 0;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float2* sA = reinterpret_cast<float2*>(smem_raw);
     float2* sB = sA + C::NA;
@@ -208,7 +210,7 @@ k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) 
         float2 x[8];
         float2 acc = make_float2(0.0f, 0.0f);
         if (staged) {
-            if (tid == 0 && l < l1) issue_prefetch(l + 1, buf ^ 1);   // buffer buf^1 was last read two barriers ago
+            if (tid == T_PREFETCH && l < l1) issue_prefetch(l + 1, buf ^ 1);   // buffer buf^1 was last read two barriers ago
             mbar_wait(&s_bar[buf], uint32_t(it >> 1) & 1u);
             const unsigned long long a = frame_abs0 + (unsigned long long)(l) * TSYM;
             const uint32_t shift = uint32_t(((a & D.ring_mask) * BPS) & 15ull);
@@ -340,7 +342,7 @@ k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) 
             }
             dft8<false>(x);
         }
-        if (own && tid == 0) {
+        if (own && tid == T_PHASE) {
             float2 t = make_float2(0.0f, 0.0f);
 #pragma unroll
             for (int w = 0; w < C::WARPS; w++) { t.x += s_part[w].x; t.y += s_part[w].y; }
