@@ -9,8 +9,10 @@ print("$1", "ms/step", round(d["ms_per_step"],4), {k: round(v/d["steps"],4) for 
 PY
 }
 DABGPU_LANES_CTAS=2 DABGPU_DEMOD_CTAS=2 run l2_d2
-DABGPU_LANES_CTAS=2 DABGPU_DEMOD_CTAS=3 run l2_d3
-DABGPU_LANES_CTAS=2 DABGPU_DEMOD_CTAS=4 run l2_d4
+DABGPU_LANES_CTAS=3 DABGPU_DEMOD_CTAS=1 run l3_d1
+DABGPU_LANES_CTAS=3 DABGPU_DEMOD_CTAS=2 run l3_d2
 DABGPU_LANES_CTAS=3 DABGPU_DEMOD_CTAS=3 run l3_d3
-DABGPU_LANES_CTAS=4 DABGPU_DEMOD_CTAS=3 run l4_d3
-DABGPU_LANES_CTAS=2 DABGPU_DEMOD_CTAS=2 run l2_d2_again
+DABGPU_LANES_CTAS=3 DABGPU_DEMOD_CTAS=4 run l3_d4
+DABGPU_LANES_CTAS=4 DABGPU_DEMOD_CTAS=4 run l4_d4
+DABGPU_LANES_CTAS=2 DABGPU_DEMOD_CTAS=3 run l2_d3
+DABGPU_CHAN_INLINE=1 run inline

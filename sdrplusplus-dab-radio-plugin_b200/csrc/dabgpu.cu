@@ -64,7 +64,6 @@ struct dabgpu_ctx {
     cudaStream_t s_dp = nullptr;
     cudaEvent_t ev_dp = nullptr, ev_dp_fork = nullptr;
     bool dp_pending = false;
-    bool ofdm_since_chan = false;   // the OFDM stage ran since the last channel decode: the two stages alternate (receiver loop)
 
     // OFDM
     OfdmState ofdm;
@@ -457,12 +456,12 @@ static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, 
                                                                                             ctx->d_vlscratch.as<uint2>(), ctx->vl_scratch_rows,
                                                                                             ctx->d_prbs.as<uint32_t>(), kc);
         } else {
-            // CTAs per SM.  On its own the kernel is fastest on three, not the four that fit (1.12 against 1.21 ms per 1024-stream
-            // call: three warps per sub-partition each run faster, the short second wave costs less than that gains).  In a
-            // receiver loop the OFDM stage of the next step runs on the other stream meanwhile: then two CTAs per SM, with the
-            // demodulator capped at two as well, so that the two kernels always share every SM half and half (2.52 ms per
-            // 1024-stream step against 2.58 for three + three and 2.87 run one after the other; profiles/r2_coresidency_*.txt)
-            int per_sm = ctx->ofdm_since_chan ? 2 : 3;
+            // Three CTAs per SM, not the four that fit: 1.12 against 1.21 ms per 1024-stream call on its own (three warps per
+            // sub-partition each run faster, the short second wave costs less than that gains).  In a receiver loop the OFDM stage
+            // of the next step runs on the other stream meanwhile; the demodulator is then capped at three CTAs per SM as well, so
+            // that one of its CTAs always fits beside the lane kernel's three: 2.28 ms per 1024-stream step against 2.33 for four +
+            // four, 2.45 for two + two and 2.49 run one after the other (profiles/r2_coresidency_c.txt).
+            int per_sm = 3;
             // a call with slightly more groups than warps would run a second, nearly empty wave of whole trellises: one CTA more
             {
                 const uint32_t slots = uint32_t(ctx->num_sms) * VL_WARPS_PER_BLOCK * uint32_t(per_sm);
@@ -913,9 +912,7 @@ int dabgpu_chan_decode(dabgpu_ctx* ctx, int first, int n) {
         CUDA_TRY(cudaStreamWaitEvent(ctx->s_dp, ctx->ev_dp_fork, 0));
         ctx->stream = ctx->s_dp;
     }
-    if (!fork) ctx->ofdm_since_chan = false;   // nothing overlaps an inline decode
     rc = chan_decode_body(ctx, first, n);
-    ctx->ofdm_since_chan = false;
     if (fork) {
         ctx->stream = main_stream;
         if (cudaEventRecord(ctx->ev_dp, ctx->s_dp) == cudaSuccess) ctx->dp_pending = true;
@@ -1154,8 +1151,7 @@ int dabgpu_ofdm_process(dabgpu_ctx* ctx, const void* iq_host, size_t stride_byte
     if (!iq_host || n_samples < 0) return set_error(DABGPU_ERR_INVALID, "bad IQ buffer");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     CUDA_TRY(join_if_many_frames(ctx, n_samples));
-    ctx->ofdm.demod_ctas_cap = ctx->dp_pending ? 2 : 0;   // a channel decode is running on its stream: share the SMs with it
-    ctx->ofdm_since_chan = true;
+    ctx->ofdm.demod_ctas_cap = ctx->dp_pending ? 3 : 0;   // a channel decode is running on its stream: share the SMs with it
     return ofdm_process(ctx->ofdm, iq_host, stride_bytes, first, n, n_samples, block_size, ctx->stream);
 }
 
@@ -1170,8 +1166,7 @@ int dabgpu_ofdm_advance(dabgpu_ctx* ctx, int first, int n, int n_samples, int bl
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     CUDA_TRY(join_if_many_frames(ctx, n_samples));
-    ctx->ofdm.demod_ctas_cap = ctx->dp_pending ? 2 : 0;   // a channel decode is running on its stream: share the SMs with it
-    ctx->ofdm_since_chan = true;
+    ctx->ofdm.demod_ctas_cap = ctx->dp_pending ? 3 : 0;   // a channel decode is running on its stream: share the SMs with it
     return ofdm_advance(ctx->ofdm, first, n, n_samples, block_size, ctx->stream);
 }
 
@@ -1326,8 +1321,7 @@ int dabgpu_submit(dabgpu_ctx* ctx, const dabgpu_step* st, uint64_t* ticket) {
     // (2) compute
     CUDA_TRY(cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0));
     const int bs = st->block_size > 0 ? st->block_size : st->n_samples;
-    ctx->ofdm.demod_ctas_cap = ctx->dp_pending ? 2 : 0;   // a channel decode is running on its stream: share the SMs with it
-    ctx->ofdm_since_chan = true;
+    ctx->ofdm.demod_ctas_cap = ctx->dp_pending ? 3 : 0;   // a channel decode is running on its stream: share the SMs with it
     if ((rc = ofdm_run(O, first, n, st->n_samples, bs, ctx->stream))) return rc;
     if (st->frames_host || st->produced_host) {
         if ((rc = sl.d_stage.alloc(size_t(n) * fb))) return rc;

@@ -165,6 +165,14 @@ template <bool INV> __device__ __forceinline__ void dft8(float2 (&a)[8]) {
     a[1] = c0; a[3] = c1; a[5] = c2; a[7] = c3;
 }
 
+// w^1 .. w^7 from one table entry.  The twiddles of a pass are powers of one root per thread; fetching them from the table
+// cost seven loads with a different 32-byte sector per lane (strides of 32 k bytes): those loads, not arithmetic or barriers, were
+// what bounded the kernel -- 1.03 -> 0.73 ms per 1024 frames with six complex multiplies instead.
+__device__ __forceinline__ void tw_powers7(const float2 w1, float2 (&w)[8]) {
+    w[1] = w1; w[2] = cmulf(w1, w1); w[3] = cmulf(w[2], w1); w[4] = cmulf(w[2], w[2]);
+    w[5] = cmulf(w[4], w1); w[6] = cmulf(w[3], w[3]); w[7] = cmulf(w[4], w[3]);
+}
+
 template <bool INV> __device__ __forceinline__ float2 ld_tw(const float2* __restrict__ tw, const int idx) {
     float2 w = __ldg(tw + idx);
     if (INV) w.y = -w.y;
@@ -175,12 +183,16 @@ template <int N, bool INV>
 __device__ __forceinline__ void fft_cta(float2 (&x)[8], float* __restrict__ re, float* __restrict__ im, const float2* __restrict__ tw, const int tid) {
     constexpr int NT = N / 8;
     dft8<INV>(x);
+    {
+        float2 wp[8];
+        tw_powers7(ld_tw<INV>(tw, tid), wp);
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        float2 v = x[k];
-        if (k > 0) v = cmulf(v, ld_tw<INV>(tw, tid * k));
-        const int a = OFDM_PAD(tid + k * NT);
-        re[a] = v.x; im[a] = v.y;
+        for (int k = 0; k < 8; k++) {
+            float2 v = x[k];
+            if (k > 0) v = cmulf(v, wp[k]);
+            const int a = OFDM_PAD(tid + k * NT);
+            re[a] = v.x; im[a] = v.y;
+        }
     }
 #pragma unroll
     for (int M = N / 8; M >= 8; M /= 8) {
@@ -192,10 +204,12 @@ __device__ __forceinline__ void fft_cta(float2 (&x)[8], float* __restrict__ re, 
 #pragma unroll
         for (int j = 0; j < 8; j++) { const int a = OFDM_PAD(base + j * m8); y[j] = make_float2(re[a], im[a]); }
         dft8<INV>(y);
+        float2 wp[8];
+        if (M > 8) tw_powers7(ld_tw<INV>(tw, r * (N / M)), wp);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             float2 v = y[k];
-            if (k > 0 && M > 8) v = cmulf(v, ld_tw<INV>(tw, r * k * (N / M)));
+            if (k > 0 && M > 8) v = cmulf(v, wp[k]);
             const int a = OFDM_PAD(base + k * m8);
             re[a] = v.x; im[a] = v.y;
         }

@@ -110,7 +110,6 @@ template <int FMT> __device__ __forceinline__ float2 demod_raw_to_c32(const uint
 }
 
 __device__ __forceinline__ float2 cmul_tw(const float2 v, const float2* __restrict__ tw, const int idx) { return cmulf(v, __ldg(tw + idx)); }
-
 template <int N, int FMT>
 __global__ void __launch_bounds__(N / 8, (N == 2048) ? 4 : (N == 1024 ? 6 : 8))
 k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) {
@@ -198,6 +197,10 @@ k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) 
     const float nf6 = float(c6 & ~3), nf7 = float(c7 & ~3);
     const float kc6 = float(c6 & 3), kc7 = float(c7 & 3);
 
+    // the root of every pass's twiddles for this thread (tw[i] = exp(-2 pi j i / N)); the powers are formed where they are used
+    const float2 w_p1a = __ldg(D.tw + tid), w_p1b = __ldg(D.tw + tid + T);
+    const float2 w_p2 = __ldg(D.tw + (tid & 63) * (N / 512)), w_p3 = __ldg(D.tw + (tid & 7) * (N / 64));
+
     float2 prev[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) prev[k] = make_float2(0.0f, 0.0f);
@@ -270,12 +273,11 @@ k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) 
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int r = tid + h * T;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    float2 v = x[2 * k + h];
-                    if (k > 0) v = cmul_tw(v, D.tw, r * k);
-                    sA[DEMOD_PADA(k * (N / 4) + r)] = v;
-                }
+                const float2 w1 = h ? w_p1b : w_p1a, w2 = cmulf(w1, w1), w3 = cmulf(w2, w1);
+                sA[DEMOD_PADA(r)] = x[h];
+                sA[DEMOD_PADA(N / 4 + r)] = cmulf(x[2 + h], w1);
+                sA[DEMOD_PADA(2 * (N / 4) + r)] = cmulf(x[4 + h], w2);
+                sA[DEMOD_PADA(3 * (N / 4) + r)] = cmulf(x[6 + h], w3);
             }
         } else if (C::R1 == 2) {
 #pragma unroll
@@ -287,10 +289,12 @@ k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) 
             }
         } else {
             dft8<false>(x);
+            float2 wp[8];
+            tw_powers7(w_p1a, wp);
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 float2 v = x[k];
-                if (k > 0) v = cmul_tw(v, D.tw, tid * k);
+                if (k > 0) v = cmulf(v, wp[k]);
                 sA[DEMOD_PADA(k * (N / 8) + tid)] = v;
             }
         }
@@ -300,13 +304,15 @@ k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) 
             const int q = tid >> 6, r = tid & 63;
             const int base = q * 512 + r;
             float2 y[8];
+            float2 wp[8];
+            tw_powers7(w_p2, wp);
 #pragma unroll
             for (int j = 0; j < 8; j++) y[j] = sA[DEMOD_PADA(base + j * 64)];
             dft8<false>(y);
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 float2 v = y[k];
-                if (k > 0) v = cmul_tw(v, D.tw, r * k * (N / 512));
+                if (k > 0) v = cmulf(v, wp[k]);
                 sA[DEMOD_PADA(base + k * 64)] = v;
             }
             // (2) a block of 512 points belongs to the 64 threads with the same q, in this pass and in the next one: only those
@@ -318,13 +324,15 @@ k_ofdm_demod2(const OfdmDev D, const int first_stream, const int sym_per_chunk) 
             const int q = tid >> 3, r = tid & 7;
             const int base = q * 64 + r;
             float2 y[8];
+            float2 wp[8];
+            tw_powers7(w_p3, wp);
 #pragma unroll
             for (int j = 0; j < 8; j++) y[j] = sA[DEMOD_PADA(base + j * 8)];
             dft8<false>(y);
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 float2 v = y[k];
-                if (k > 0) v = cmul_tw(v, D.tw, r * k * (N / 64));
+                if (k > 0) v = cmulf(v, wp[k]);
                 sB[DEMOD_L3(base + k * 8)] = v;
             }
         }
