@@ -238,6 +238,9 @@ k_vit_prep(const VitJobDev* __restrict__ jobs, VlPlan* __restrict__ plan, const 
                 for (uint32_t j = 0; j < VP_UNIT / 16u; j++) {
                     const uint32_t wbase = h + 4u * j;
                     L[wbase + 0u][lane] = P[j].x; L[wbase + 1u][lane] = P[j].y; L[wbase + 2u][lane] = P[j].z; L[wbase + 3u][lane] = P[j].w;
+                    // the -128 test runs on the punctured input (at most as many words as steps, half as many at rate 1/2); the
+                    // unit may hold a few bytes of a neighbouring trellis: a false alarm only selects the general decoder form
+                    m128 = m128 || vl_has_m128(P[j].x) || vl_has_m128(P[j].y) || vl_has_m128(P[j].z) || vl_has_m128(P[j].w);
                 }
                 if (h == 0u) {
 #pragma unroll
@@ -258,7 +261,6 @@ k_vit_prep(const VitJobDev* __restrict__ jobs, VlPlan* __restrict__ plan, const 
                     const uint32_t g8 = (t - S.start) & 7u;
                     word = prep_word(L, lane, origin + prep_in_index(S, t), (S.cntw >> (4u * g8)) & 0xFu);
                 }
-                m128 = m128 || vl_has_m128(word);
                 dst[size_t(t) * 32u] = word;
             }
             __syncwarp();
@@ -301,10 +303,8 @@ k_vit_prep(const VitJobDev* __restrict__ jobs, VlPlan* __restrict__ plan, const 
                 }
             }
 #pragma unroll
-            for (uint32_t g8 = 0; g8 < 8u; g8++) {
-                m128 = m128 || vl_has_m128(words[g8]);
+            for (uint32_t g8 = 0; g8 < 8u; g8++)
                 if (tp + g8 < padded) dst[size_t(tp + g8) * 32u] = words[g8];
-            }
         }
         __syncwarp();
     }
