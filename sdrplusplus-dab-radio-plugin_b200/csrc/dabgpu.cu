@@ -404,6 +404,10 @@ struct VlBound {
     }
 };
 
+#ifndef VL_TB_WIDE
+#define VL_TB_WIDE 10u   // traceback rows per batch of the 128-register lane kernel (two batches in flight); 15 / 20 / 25 rows hide more of
+                         // the decision loads' latency but spill in the forward loop: 1.26 / 1.25 / 1.39 ms against 1.13
+#endif
 static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, const VlBound* bound, bool precounted = false) {
     CUDA_TRY(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
     VlPlan* plan = nullptr;
@@ -468,7 +472,7 @@ static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, 
                 if (groups > slots && groups * 4u < slots * 5u) per_sm++;
             }
             if (const char* e = getenv("DABGPU_LANES_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 4) per_sm = v; }   // tuning knob
-            k_viterbi_lanes<10u, 4><<<ctx->num_sms * per_sm, VL_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(), ctx->d_vlsym.as<uint32_t>(),
+            k_viterbi_lanes<VL_TB_WIDE, 4><<<ctx->num_sms * per_sm, VL_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(d_jobs, plan, ctx->d_vllist.as<uint32_t>(), ctx->d_vlsym.as<uint32_t>(),
                                                                                                 ctx->d_vlscratch.as<uint2>(), ctx->vl_scratch_rows,
                                                                                                 ctx->d_prbs.as<uint32_t>(), kc);
         }
