@@ -512,7 +512,8 @@ def main():
         ach = frames_ * OFDM_ALG_BYTES / (t * 1e-3) / 1e9 if t > 0 else 0.0
         k = ncu.get("k_ofdm_demod2", {})
         return {"kernel": "k_ofdm_demod2<2048,u8>", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": k["dram_bytes_per_frame"] * frames_ / max(n, 1) if "dram_bytes_per_frame" in k else None,
+                # per launch that has work: one frame of every stream (the launch count also holds the empty launches of a step)
+                "traffic": k["dram_bytes_per_frame"] * S if "dram_bytes_per_frame" in k else None,
                 "algorithmic_bytes_per_frame": OFDM_ALG_BYTES, "frames_in_profiled_pass": frames_, "kernel_ms_total": t, "kernel_launches": n,
                 "kernel_share_of_step": t / ms_prof_ if ms_prof_ > 0 else None,
                 "issue": {"warp_inst_per_sample": k.get("warp_inst_per_sample"), "issue_active_pct": k.get("issue_active_pct"),
