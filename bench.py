@@ -229,6 +229,17 @@ def _workload_name(args):
     return ("full_chain_mode1_" if args.workload == "full" else "ofdm_demod_mode1_") + f"{args.streams}_streams_per_gpu"
 
 
+def _config(args):
+    """The workload both arms measure (BASELINE.json configs[3] per GPU by default)."""
+    S, full = args.streams, args.workload == "full"
+    return {"workload": _workload_name(args),
+            "streams_per_gpu": S, "frame_samples": FRAME_SAMPLES, "process_block": BLOCK, "iq_format": "u8",
+            "ensemble": "FIC + 18 x EEP 3-A 48 CU DAB+ sub-channels per stream" if full else "n/a",
+            "cache": f"inputs larger than L2: every step reads {S * FRAME_SAMPLES * 2 / 1e6:.0f} MB of IQ last touched {PERIOD_FRAMES} steps ago",
+            "snr_db": 15, "cfo": "uniform +-20 kHz", "timing": "uniform lead in [0, 196608)",
+            "signal_period_frames": PERIOD_FRAMES}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -245,8 +256,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "dab_mode1_iq_msps", "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_dt / max(len(vals), 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": _workload_name(args),
-                   "note": "the reference's own CPU code on all host cores, bounded sample per step; " + FFT_SHIM_NOTE},
+        "config": _config(args),   # the same keys and values as our arm: the workload is the same, the sample of it is bounded
+        "note": "the reference's own CPU code on all host cores, bounded sample of the workload per step; " + FFT_SHIM_NOTE,
         "realtime_streams": v / 2.048,
         "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -555,12 +566,7 @@ def main():
         "metric": "dab_mode1_iq_msps", "value": value, "unit": "MS/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (OFDM) / u16 (Viterbi) / u8 (RS)",
         "data": "synthetic",
-        "config": {"workload": _workload_name(args),
-                   "streams_per_gpu": S, "frame_samples": FRAME_SAMPLES, "process_block": BLOCK, "iq_format": "u8",
-                   "ensemble": "FIC + 18 x EEP 3-A 48 CU DAB+ sub-channels per stream" if full else "n/a",
-                   "cache": f"inputs larger than L2: every step reads {S * FRAME_SAMPLES * 2 / 1e6:.0f} MB of IQ last touched {PERIOD_FRAMES} steps ago",
-                   "snr_db": 15, "cfo": "uniform +-20 kHz", "timing": "uniform lead in [0, 196608)",
-                   "signal_period_frames": PERIOD_FRAMES},
+        "config": _config(args),
         "realtime_streams": value / 2.048,
         "frames_demodulated": frames_all,
         "e2e": None if Ke <= 0 else {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
