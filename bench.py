@@ -43,6 +43,8 @@ BLOCK = 65536
 PERIOD_FRAMES = 10                          # 40 CIFs = 8 superframes: the synthetic transmission repeats after this many frames
 # SURVEY.md 8(d), per Mode I frame
 OFDM_ALG_BYTES = 393216 + 230400            # u8 IQ in + int8 soft bits out
+OFDM_ALG_BYTES_C32 = 1572864 + 230400       # complex<float> IQ in + int8 soft bits out (9.172 B/sample)
+OFDM_ALG_FLOP = 17.7e6                      # floating-point operations per Mode I frame
 VIT_ALG_BYTES = 230400 + (110592 + 3072) // 8   # soft bits in + decoded bytes out (decisions stay on chip)
 VIT_STEPS_PER_FRAME = 72 * 1542 + 4 * 774   # trellis steps of the full ensemble: 18 x 4 sub-channel CIFs + 4 FIB groups
 VIT_BITS_PER_FRAME = 110592 + 3072          # decoded information bits
@@ -176,7 +178,8 @@ def cpu_reference(n_threads: int, frames_per_thread: int, target_seconds: float,
     """Times the reference's own code (oracle/_ref, unmodified sources) or, if that library is absent, the C port, one
     independent receiver per thread on `n_threads` host threads.  Full workload: OFDM_Demod -> FIC_Decoder + 18 x MSC_Decoder
     (EEP 3-A) + 18 x AAC_Frame_Processor, i.e. what the GPU does per stream.  OFDM workload: OFDM_Demod only.
-    Returns (MS/s, kind, sample description, wall seconds)."""
+    Returns (MS/s, kind, sample description, wall seconds, per-core figures or None).  The per-core figures are one
+    receiver alone on one core: MS/s and the ms per frame spent in the OFDM demodulator, FIC decoder, MSC decoders and DAB+ processors."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import pyref
@@ -209,6 +212,15 @@ def cpu_reference(n_threads: int, frames_per_thread: int, target_seconds: float,
         run = lambda rep: L.dabo_time_ofdm_u8(1, u8, n_samples, BLOCK, rep, None)
     t_one = run(1)     # warm-up + calibration of the bounded sample
     t_one = run(1)
+    per_core = None
+    if use_chain and hasattr(L, "ref_time_chain_split_u8"):
+        cnt, split = np.zeros(8, dtype=np.int64), np.zeros(4, dtype=np.float64)
+        rep1 = max(1, int(1.5 / max(t_one, 1e-4)))
+        t1 = L.ref_time_chain_split_u8(1, u8, n_samples, BLOCK, rep1, sub_arr, len(subs), cnt, split)
+        nf = max(int(cnt[0]), 1)
+        per_core = {"value": rep1 * n_samples / t1 / 1e6, "unit": "MS/s", "cores": 1, "frames": int(cnt[0]),
+                    "ms_per_frame": {"total": 1e3 * t1 / nf, "ofdm": 1e3 * split[0] / nf, "fic": 1e3 * split[1] / nf,
+                                     "msc": 1e3 * split[2] / nf, "dabplus_rs": 1e3 * split[3] / nf}}
     repeat = max(2, int(target_seconds / max(t_one, 1e-4)))
     fn = lambda: run(repeat)
     t0 = time.perf_counter()
@@ -222,7 +234,7 @@ def cpu_reference(n_threads: int, frames_per_thread: int, target_seconds: float,
     sample = (f"{n_threads} independent Mode I streams x {repeat}x{frames_per_thread} frames u8 IQ through {what} "
               f"(threads=1 as in the plugin, blocks of {BLOCK}), one receiver per host thread, {dt:.1f} s wall; "
               + (FFT_SHIM_NOTE if kind == "reference" else "C restatement of the chain (oracle/dab_oracle.c)"))
-    return msps, kind, sample, dt
+    return msps, kind, sample, dt, per_core
 
 
 def _workload_name(args):
@@ -247,7 +259,7 @@ def run_reference(args, rank, world):
     vals, total_dt = [], 0.0
     sample = kind = ""
     for i in range(args.warmup + args.steps):
-        msps, kind, sample, dt = cpu_reference(cores, 20, 4.0, full=args.workload == "full")
+        msps, kind, sample, dt, per_core = cpu_reference(cores, 20, 4.0, full=args.workload == "full")
         if i >= args.warmup:
             vals.append(msps)
             total_dt += dt
@@ -259,7 +271,7 @@ def run_reference(args, rank, world):
         "config": _config(args),   # the same keys and values as our arm: the workload is the same, the sample of it is bounded
         "note": "the reference's own CPU code on all host cores, bounded sample of the workload per step; " + FFT_SHIM_NOTE,
         "realtime_streams": v / 2.048,
-        "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": kind, "sample": sample, "per_core": per_core},
         "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -330,6 +342,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spot-check", action="store_true")
     ap.add_argument("--no-ofdm-leg", action="store_true", help="full workload: skip the OFDM-only sub-leg")
+    ap.add_argument("--no-c32-leg", action="store_true", help="skip the OFDM-only sub-leg with complex<float> input (256 streams)")
     ap.add_argument("--wc-host", action="store_true", help="e2e: write-combined pinned memory for the IQ the host feeds in")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -379,7 +392,11 @@ def main():
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
 
-    def make_ctx(with_chan):
+    def make_ctx(with_chan, c32=None):
+        if c32 is not None:      # the plugin's own input format: complex<float> from dsp::complex_t (src/dab_module.cpp:20-28)
+            g = pkg.DabGpu(mode=1, max_streams=c32.shape[0], device=local_rank, iq_format=pkg.IQ_C32, cuda_stream=stream.cuda_stream)
+            g.ofdm_attach_device_input(c32.data_ptr(), c32.shape[1] // 2, c32.shape[1] // 2)
+            return g
         g = pkg.DabGpu(mode=1, max_streams=S, device=local_rank, cuda_stream=stream.cuda_stream)
         g.ofdm_attach_device_input(iq.data_ptr(), total_samples, total_samples)
         if with_chan:
@@ -387,9 +404,9 @@ def main():
                 g.msc_configure(s, subs)
         return g
 
-    def run_leg(with_chan):
+    def run_leg(with_chan, K=K, c32=None):
         """W warm-up steps, K timed steps (device-resident), K profiled steps.  Returns a dict of raw measurements."""
-        g = make_ctx(with_chan)
+        g = make_ctx(with_chan, c32)
 
         def step():
             g.ofdm_advance(FRAME_SAMPLES, block_size=BLOCK)
@@ -517,19 +534,24 @@ def main():
     sm_hz = (clocks["sm_mhz"] or 1965.0) * 1e6
     n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
 
-    def roofline_ofdm(prof_, frames_, ms_prof_):
+    def roofline_ofdm(prof_, frames_, ms_prof_, c32=False):
         t = prof_["ofdm_demod"]["ms"]
         n = prof_["ofdm_demod"]["launches"]
-        ach = frames_ * OFDM_ALG_BYTES / (t * 1e-3) / 1e9 if t > 0 else 0.0
+        alg = OFDM_ALG_BYTES_C32 if c32 else OFDM_ALG_BYTES
+        ach = frames_ * alg / (t * 1e-3) / 1e9 if t > 0 else 0.0
         k = ncu.get("k_ofdm_demod2", {})
-        return {"kernel": "k_ofdm_demod2<2048,u8>", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        return {"kernel": "k_ofdm_demod2<2048,c32>" if c32 else "k_ofdm_demod2<2048,u8>", "bound": "hbm", "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak,
                 # per launch that has work: one frame of every stream (the launch count also holds the empty launches of a step)
-                "traffic": k["dram_bytes_per_frame"] * S if "dram_bytes_per_frame" in k else None,
-                "algorithmic_bytes_per_frame": OFDM_ALG_BYTES, "frames_in_profiled_pass": frames_, "kernel_ms_total": t, "kernel_launches": n,
+                "traffic": k["dram_bytes_per_frame"] * S if ("dram_bytes_per_frame" in k and not c32) else None,
+                "algorithmic_bytes_per_frame": alg, "frames_in_profiled_pass": frames_, "kernel_ms_total": t, "kernel_launches": n,
                 "kernel_share_of_step": t / ms_prof_ if ms_prof_ > 0 else None,
                 "issue": {"warp_inst_per_sample": k.get("warp_inst_per_sample"), "issue_active_pct": k.get("issue_active_pct"),
+                          # ~17.7 M floating-point operations per Mode I frame (FFT 8.56, PLL 6.9, sync 0.56, CP 0.31, DQPSK 1.4)
+                          "fp32_tflops_algorithmic": frames_ * OFDM_ALG_FLOP / (t * 1e-3) / 1e12 if t > 0 else None,
                           "source": k.get("source")},
-                "note": "u8 input makes this kernel FP32-issue bound (~100 instructions per sample), not HBM bound; see DESIGN.md"}
+                "note": ("c32 input (the plugin's own format, 8 B/sample): " if c32 else "u8 input (2 B/sample): ") +
+                        "this kernel is FP32-issue bound (~100 instructions per sample), not HBM bound; see DESIGN.md"}
 
     def roofline_viterbi():
         t = prof["viterbi"]["ms"]
@@ -595,6 +617,22 @@ def main():
             line["ofdm_only"] = {"workload": f"ofdm_demod_mode1_{S}_streams_per_gpu", "ms_per_step": ms_o / K,
                                  "iq_msps": world * S * FRAME_SAMPLES * K / (ms_o * 1e-3) / 1e6, "kernel_ms": {k: v["ms"] for k, v in leg["prof"].items()},
                                  "roofline": roofline_ofdm(leg["prof"], fr, leg["ms_prof"])}
+    if not args.no_c32_leg:
+        # the same OFDM workload fed as complex<float> (what SDR++ hands the plugin): 9.17 instead of 3.17 algorithmic bytes per sample
+        Sc, Kc = min(S, 256), min(K, 20)
+        reps_c = (W + 2 * Kc + 2 + PERIOD_FRAMES - 1) // PERIOD_FRAMES
+        c32 = torch.empty((Sc, 2 * reps_c * PERIOD_FRAMES * FRAME_SAMPLES), dtype=torch.float32, device=dev)
+        for s_ in range(Sc):        # the conversion of app_iq_readers.h:23-43: (u8 - 127.5) * (1 / 127.5)
+            c32[s_] = ((cyc[s_].to(torch.float32) - 127.5) * np.float32(1.0 / 127.5)).repeat(reps_c)
+        torch.cuda.synchronize()
+        leg = run_leg(False, K=Kc, c32=c32)
+        fr = leg["c2"]["frames_demodulated"] - leg["c1"]["frames_demodulated"]
+        ms_c = allmax(leg["ms"])
+        line["ofdm_only_c32"] = {"workload": f"ofdm_demod_mode1_{Sc}_streams_per_gpu_c32_input", "steps": Kc, "ms_per_step": ms_c / Kc,
+                                 "iq_msps": world * Sc * FRAME_SAMPLES * Kc / (ms_c * 1e-3) / 1e6,
+                                 "kernel_ms": {k: v["ms"] for k, v in leg["prof"].items()},
+                                 "roofline": roofline_ofdm(leg["prof"], fr, leg["ms_prof"], c32=True)}
+        del c32
     # cuFFT as the stated comparison point of the FFT stage: a batched 2048-point C2C transform of as many symbols as one step
     # demodulates, c32 in HBM -> c32 in HBM (torch.fft = cuFFT), against the whole fused kernel that also does PLL, CP
     # correlation, DQPSK, de-interleave and quantisation and moves 2 + 1.17 instead of 8 + 8 bytes per sample
@@ -630,8 +668,8 @@ def main():
         if hasattr(os, "sched_setaffinity"):
             os.sched_setaffinity(0, _ALL_CPUS)      # the CPU arm uses every host core again
         cores = len(_ALL_CPUS)
-        v, kind, sample, _ = cpu_reference(cores, 20, 12.0, full=full)
-        line["cpu_baseline"] = {"value": v, "unit": "MS/s", "cores": cores, "kind": kind, "sample": sample}
+        v, kind, sample, _, per_core = cpu_reference(cores, 20, 12.0, full=full)
+        line["cpu_baseline"] = {"value": v, "unit": "MS/s", "cores": cores, "kind": kind, "sample": sample, "per_core": per_core}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

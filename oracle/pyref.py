@@ -106,6 +106,11 @@ class RefLib:
             L.ref_time_chain_u8.argtypes = [C.c_int, _u8p, C.c_long, C.c_int, C.c_int, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"), C.c_int,
                                             np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
             L.ref_time_chain_u8.restype = C.c_double
+        if hasattr(L, "ref_time_chain_split_u8"):
+            L.ref_time_chain_split_u8.argtypes = [C.c_int, _u8p, C.c_long, C.c_int, C.c_int, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"), C.c_int,
+                                                  np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"),
+                                                  np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")]
+            L.ref_time_chain_split_u8.restype = C.c_double
 
         if hasattr(L, "ref_iq_convert"):
             L.ref_iq_convert.argtypes = [C.c_char_p, _u8p, C.c_size_t, _f32p, C.c_size_t]

@@ -548,8 +548,13 @@ API double ref_time_ofdm_u8(int mode, const uint8_t* iq, long n_samples, int blo
 // DAB+ sub-channels.  subs = n_subs x {start_address, length, is_uep, uep_index, eep_level, eep_type_b, is_dabplus}.
 // counts_out[8] = {frames, fibs_ok, msc_bytes, access_units, superframe headers, RS errors, AU CRC errors, firecode errors} (observer
 // events of all sub-channels; bench.py's spot check compares them with the GPU's counters).  Returns seconds of wall time.
-API double ref_time_chain_u8(int mode, const uint8_t* iq, long n_samples, int block_size, int repeat, const int* subs, int n_subs,
-                             long long* counts_out) {
+// split_out[4] (may be NULL) = seconds spent in {OFDM_Demod::Process incl. the u8 -> float conversion, FIC_Decoder, MSC_Decoder::DecodeCIF,
+// AAC_Frame_Processor::Process (fire code, RS(120,110), AU CRCs)}: the per-stage split SURVEY.md section 8(d) asks for.
+API double ref_time_chain_split_u8(int mode, const uint8_t* iq, long n_samples, int block_size, int repeat, const int* subs, int n_subs,
+                                   long long* counts_out, double* split_out) {
+    using clk = std::chrono::steady_clock;
+    double t_ofdm = 0, t_fic = 0, t_msc = 0, t_aac = 0;
+    auto lap = [](clk::time_point& mark, double& acc) { const auto now = clk::now(); acc += std::chrono::duration<double>(now - mark).count(); mark = now; };
     int dp[13];
     if (ref_dab_params(mode, dp) != 0) return -1.0;
     const DAB_Parameters P = get_dab_parameters(mode);
@@ -570,17 +575,21 @@ API double ref_time_chain_u8(int mode, const uint8_t* iq, long n_samples, int bl
     for (int rep = 0; rep < repeat; rep++) {
         for (long off = 0; off < n_samples; off += block_size) {
             const long n = (n_samples - off < block_size) ? (n_samples - off) : block_size;
+            auto mark = clk::now();
             ref_ofdm_process_u8(r, iq + 2*off, int(n), 1);
             float cf[2]; int to;
             while (ref_ofdm_pop_frame(r, frame.data(), cf, &to) > 0) {
+                lap(mark, t_ofdm);
                 frames++;
                 if (P.nb_fib_cif_bits == 2304) {
                     for (int c = 0; c < P.nb_cifs; c++) fibs_ok += ref_fic_decode_group(fic, frame.data() + c*P.nb_fib_cif_bits, P.nb_fib_cif_bits, c, fibs.data(), 8);
                 }
+                lap(mark, t_fic);
                 for (int c = 0; c < P.nb_cifs; c++) {
                     const int8_t* cif = frame.data() + P.nb_fic_bits + c*P.nb_cif_bits;
                     for (int k = 0; k < n_subs; k++) {
                         const int nb = ref_msc_decode_cif(msc[size_t(k)], cif, P.nb_cif_bits, bytes.data(), int(bytes.size()));
+                        lap(mark, t_msc);
                         if (nb > 0) {
                             msc_bytes += nb;
                             if (aac[size_t(k)]) {
@@ -597,11 +606,13 @@ API double ref_time_chain_u8(int mode, const uint8_t* iq, long n_samples, int bl
                                     else if (hdr[0] == EV_FIRECODE_ERROR) fire++;
                                     o += 24 + ((size_t(hdr[5]) + 3u) & ~size_t(3));
                                 }
+                                lap(mark, t_aac);
                             }
                         }
                     }
                 }
             }
+            lap(mark, t_ofdm);
         }
     }
     const auto t1 = std::chrono::steady_clock::now();
@@ -609,11 +620,17 @@ API double ref_time_chain_u8(int mode, const uint8_t* iq, long n_samples, int bl
         counts_out[0] = frames; counts_out[1] = fibs_ok; counts_out[2] = msc_bytes; counts_out[3] = aus;
         counts_out[4] = headers; counts_out[5] = rs_err; counts_out[6] = au_crc; counts_out[7] = fire;
     }
+    if (split_out) { split_out[0] = t_ofdm; split_out[1] = t_fic; split_out[2] = t_msc; split_out[3] = t_aac; }
     for (auto* m : msc) ref_msc_destroy(m);
     for (auto* a : aac) if (a) ref_aac_destroy(a);
     ref_fic_destroy(fic);
     ref_ofdm_destroy(r);
     return std::chrono::duration<double>(t1-t0).count();
+}
+
+API double ref_time_chain_u8(int mode, const uint8_t* iq, long n_samples, int block_size, int repeat, const int* subs, int n_subs,
+                             long long* counts_out) {
+    return ref_time_chain_split_u8(mode, iq, n_samples, block_size, repeat, subs, n_subs, counts_out, nullptr);
 }
 
 // ---- FIG processing: FIBs -> the reference's database --------------------------------
