@@ -625,10 +625,11 @@ def default_ensemble() -> List[Subchannel]:
     return [Subchannel(id=i, start_address=48 * i, length=48, eep_level=2, eep_type_b=False) for i in range(18)]
 
 
-def periodic_frames(mode: int, subchannels: Sequence[Subchannel], seed: int, period_frames: int) -> np.ndarray:
+def periodic_frames(mode: int, subchannels: Sequence[Subchannel], seed: int, period_frames: int, return_logical: bool = False):
     """[period_frames, nb_frame_bits] coded transmission frames whose endless repetition is a valid transmission: the logical
     frames of every sub-channel repeat with the period (a whole number of 5-CIF DAB+ superframes), hence so do the
-    time-interleaved CIFs once the 16-CIF interleaver has filled.  Used to feed throughput runs of any length from a short buffer."""
+    time-interleaved CIFs once the 16-CIF interleaver has filled.  Used to feed throughput runs of any length from a short buffer.
+    return_logical: also return {sub-channel id: [period_cifs, frame_bytes]} = the bytes a decoder must give back, one period of them."""
     p = MODES[mode]
     period_cifs = period_frames * p.nb_cifs
     assert period_cifs % 5 == 0 and period_cifs >= 16, "the period must hold whole superframes and at least the interleaver depth"
@@ -644,4 +645,6 @@ def periodic_frames(mode: int, subchannels: Sequence[Subchannel], seed: int, per
 
     ens._next_logical_frame = replay
     frames = [ens.next_frame_bits() for _ in range(2 * period_frames)]
+    if return_logical:
+        return np.stack(frames[period_frames:]), {k: np.stack(v) for k, v in cache.items()}
     return np.stack(frames[period_frames:])
