@@ -249,7 +249,7 @@ def _config(args):
             "ensemble": "FIC + 18 x EEP 3-A 48 CU DAB+ sub-channels per stream" if full else "n/a",
             "cache": f"inputs larger than L2: every step reads {S * FRAME_SAMPLES * 2 / 1e6:.0f} MB of IQ last touched {PERIOD_FRAMES} steps ago",
             "snr_db": 15, "cfo": "uniform +-20 kHz", "timing": "uniform lead in [0, 196608)",
-            "signal_period_frames": PERIOD_FRAMES}
+            "signal_period_frames": PERIOD_FRAMES, "contexts_per_gpu": max(1, getattr(args, "contexts", 1))}
 
 
 def run_reference(args, rank, world):
@@ -313,7 +313,7 @@ def spot_check(pkg, tx, np, torch, cyc, subs, local_rank, stream, n_check=3, n_f
                     "from a time de-interleaver that is only partly filled with real CIFs, in the reference exactly as here"}
 
 
-def timed_pass(torch, dist, world, stream, step, K, finish=None):
+def timed_pass(torch, dist, world, stream, step, K, finish=None, start=None):
     """K steps bracketed by barrier + synchronize, CUDA events on `stream`; returns ms (this rank)."""
     torch.cuda.synchronize()
     if world > 1:
@@ -321,10 +321,12 @@ def timed_pass(torch, dist, world, stream, step, K, finish=None):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    if start is not None:
+        start()           # several contexts: their streams start behind the start event
     for _ in range(K):
         step()
     if finish is not None:
-        finish()          # the last channel decode runs on the library's channel stream: make the main stream wait for it
+        finish()          # the last channel decode runs on the library's channel stream: make the timing stream wait for it
     e1.record(stream)
     torch.cuda.synchronize()
     return e0.elapsed_time(e1)
@@ -342,6 +344,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spot-check", action="store_true")
     ap.add_argument("--no-ofdm-leg", action="store_true", help="full workload: skip the OFDM-only sub-leg")
+    ap.add_argument("--contexts", type=int, default=1, help="device-resident legs: split the streams of a GPU over this many contexts (each with its own CUDA streams)")
     ap.add_argument("--no-c32-leg", action="store_true", help="skip the OFDM-only sub-leg with complex<float> input (256 streams)")
     ap.add_argument("--wc-host", action="store_true", help="e2e: write-combined pinned memory for the IQ the host feeds in")
     args = ap.parse_args()
@@ -392,39 +395,102 @@ def main():
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
 
-    def make_ctx(with_chan, c32=None):
-        if c32 is not None:      # the plugin's own input format: complex<float> from dsp::complex_t (src/dab_module.cpp:20-28)
+    NCTX = max(1, args.contexts)
+    assert S % NCTX == 0
+
+    class CtxGroup:
+        """`NCTX` contexts of S / NCTX streams each on this GPU, every one with its own main CUDA stream (and, inside the library,
+        its own channel stream): the step of one context overlaps the step of the others.  With one context this is the plain API."""
+
+        def __init__(self, with_chan):
+            self.with_chan = with_chan
+            self.n = S // NCTX
+            self.streams = [stream] if NCTX == 1 else [torch.cuda.Stream(dev) for _ in range(NCTX)]
+            self.ctxs = []
+            self.done = [torch.cuda.Event() for _ in range(NCTX)]
+            for c in range(NCTX):
+                g = pkg.DabGpu(mode=1, max_streams=self.n, device=local_rank, cuda_stream=self.streams[c].cuda_stream)
+                g.ofdm_attach_device_input(iq.data_ptr() + c * self.n * iq.stride(0), total_samples, total_samples)
+                if with_chan:
+                    for s in range(self.n):
+                        g.msc_configure(s, subs)
+                self.ctxs.append(g)
+
+        def fork(self):      # the contexts' streams start after everything queued on the timing stream so far
+            if NCTX > 1:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                for st in self.streams:
+                    st.wait_event(ev)
+
+        def step(self):
+            for g in self.ctxs:
+                g.ofdm_advance(FRAME_SAMPLES, block_size=BLOCK)
+                if self.with_chan:
+                    g.chan_decode()
+
+        def join(self):      # the timing stream waits for every context (its channel stream included)
+            for c, g in enumerate(self.ctxs):
+                if self.with_chan:
+                    g.chan_join()
+                if NCTX > 1:
+                    self.done[c].record(self.streams[c])
+                    stream.wait_event(self.done[c])
+
+        def counters(self):
+            cs = [g.counters() for g in self.ctxs]
+            return {k: sum(c[k] for c in cs) for k in cs[0]}
+
+        @property
+        def launch_count(self):
+            return sum(g.launch_count for g in self.ctxs)
+
+        def profile_enable(self, on):
+            for g in self.ctxs:
+                g.profile_enable(on)
+
+        def profile_read(self):
+            ps = [g.profile_read() for g in self.ctxs]
+            return {k: {"ms": sum(p_[k]["ms"] for p_ in ps), "launches": sum(p_[k]["launches"] for p_ in ps)} for k in ps[0]}
+
+        def close(self):
+            for g in self.ctxs:
+                g.close()
+
+    class C32Group(CtxGroup):      # one context fed complex<float>: the plugin's own input format (src/dab_module.cpp:20-28)
+        def __init__(self, c32):
+            self.with_chan, self.n, self.streams, self.done = False, c32.shape[0], [stream], []
             g = pkg.DabGpu(mode=1, max_streams=c32.shape[0], device=local_rank, iq_format=pkg.IQ_C32, cuda_stream=stream.cuda_stream)
             g.ofdm_attach_device_input(c32.data_ptr(), c32.shape[1] // 2, c32.shape[1] // 2)
-            return g
-        g = pkg.DabGpu(mode=1, max_streams=S, device=local_rank, cuda_stream=stream.cuda_stream)
-        g.ofdm_attach_device_input(iq.data_ptr(), total_samples, total_samples)
-        if with_chan:
-            for s in range(S):
-                g.msc_configure(s, subs)
-        return g
+            self.ctxs = [g]
+
+        def fork(self):
+            pass
+
+        def join(self):
+            pass
 
     def run_leg(with_chan, K=K, c32=None):
         """W warm-up steps, K timed steps (device-resident), K profiled steps.  Returns a dict of raw measurements."""
-        g = make_ctx(with_chan, c32)
+        g = CtxGroup(with_chan) if c32 is None else C32Group(c32)
 
         def step():
-            g.ofdm_advance(FRAME_SAMPLES, block_size=BLOCK)
-            if with_chan:
-                g.chan_decode()
+            g.step()
 
+        g.fork()
         for _ in range(W):
             step()
+        g.join()
         torch.cuda.synchronize()
         c0 = g.counters()
         launches0 = g.launch_count
-        ms = timed_pass(torch, dist, world, stream, step, K, finish=g.chan_join if with_chan else None)
+        ms = timed_pass(torch, dist, world, stream, step, K, finish=g.join, start=g.fork)
         c1 = g.counters()
         launches = g.launch_count - launches0
         # second pass with CUDA events around every kernel launch (dabgpu_profile_*): per-kernel times for the roofline.  The
         # library keeps the channel decode on the main stream while profiling, so this pass is slower than the one above.
         g.profile_enable(True)
-        ms_prof = timed_pass(torch, dist, world, stream, step, K)
+        ms_prof = timed_pass(torch, dist, world, stream, step, K, finish=g.join, start=g.fork)
         prof = g.profile_read()
         g.profile_enable(False)
         c2 = g.counters()
