@@ -402,9 +402,9 @@ def main():
         """`NCTX` contexts of S / NCTX streams each on this GPU, every one with its own main CUDA stream (and, inside the library,
         its own channel stream): the step of one context overlaps the step of the others.  With one context this is the plain API."""
 
-        def __init__(self, with_chan):
+        def __init__(self, with_chan, n_streams=None):
             self.with_chan = with_chan
-            self.n = S // NCTX
+            self.n = (n_streams or S) // NCTX
             self.streams = [stream] if NCTX == 1 else [torch.cuda.Stream(dev) for _ in range(NCTX)]
             self.ctxs = []
             self.done = [torch.cuda.Event() for _ in range(NCTX)]
@@ -470,9 +470,9 @@ def main():
         def join(self):
             pass
 
-    def run_leg(with_chan, K=K, c32=None):
+    def run_leg(with_chan, K=K, c32=None, n_streams=None):
         """W warm-up steps, K timed steps (device-resident), K profiled steps.  Returns a dict of raw measurements."""
-        g = CtxGroup(with_chan) if c32 is None else C32Group(c32)
+        g = CtxGroup(with_chan, n_streams) if c32 is None else C32Group(c32)
 
         def step():
             g.step()
@@ -600,7 +600,7 @@ def main():
     sm_hz = (clocks["sm_mhz"] or 1965.0) * 1e6
     n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
 
-    def roofline_ofdm(prof_, frames_, ms_prof_, c32=False):
+    def roofline_ofdm(prof_, frames_, ms_prof_, c32=False, n_streams=None):
         t = prof_["ofdm_demod"]["ms"]
         n = prof_["ofdm_demod"]["launches"]
         alg = OFDM_ALG_BYTES_C32 if c32 else OFDM_ALG_BYTES
@@ -609,7 +609,7 @@ def main():
         return {"kernel": "k_ofdm_demod2<2048,c32>" if c32 else "k_ofdm_demod2<2048,u8>", "bound": "hbm", "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak,
                 # per launch that has work: one frame of every stream (the launch count also holds the empty launches of a step)
-                "traffic": k["dram_bytes_per_frame"] * S if ("dram_bytes_per_frame" in k and not c32) else None,
+                "traffic": k["dram_bytes_per_frame"] * (n_streams or S) if ("dram_bytes_per_frame" in k and not c32) else None,
                 "algorithmic_bytes_per_frame": alg, "frames_in_profiled_pass": frames_, "kernel_ms_total": t, "kernel_launches": n,
                 "kernel_share_of_step": t / ms_prof_ if ms_prof_ > 0 else None,
                 "issue": {"warp_inst_per_sample": k.get("warp_inst_per_sample"), "issue_active_pct": k.get("issue_active_pct"),
@@ -683,6 +683,14 @@ def main():
             line["ofdm_only"] = {"workload": f"ofdm_demod_mode1_{S}_streams_per_gpu", "ms_per_step": ms_o / K,
                                  "iq_msps": world * S * FRAME_SAMPLES * K / (ms_o * 1e-3) / 1e6, "kernel_ms": {k: v["ms"] for k, v in leg["prof"].items()},
                                  "roofline": roofline_ofdm(leg["prof"], fr, leg["ms_prof"])}
+    if not args.no_ofdm_leg and S > 256 and NCTX == 1:
+        # BASELINE.json configs[1] as it is written: OFDM demodulation only, 256 Mode I streams on one GPU
+        leg = run_leg(False, n_streams=256)
+        fr = leg["c2"]["frames_demodulated"] - leg["c1"]["frames_demodulated"]
+        ms_o = allmax(leg["ms"])
+        line["ofdm_only_256"] = {"workload": "ofdm_demod_mode1_256_streams_per_gpu", "ms_per_step": ms_o / K,
+                                 "iq_msps": world * 256 * FRAME_SAMPLES * K / (ms_o * 1e-3) / 1e6, "kernel_ms": {k: v["ms"] for k, v in leg["prof"].items()},
+                                 "roofline": roofline_ofdm(leg["prof"], fr, leg["ms_prof"], n_streams=256)}
     if not args.no_c32_leg:
         # the same OFDM workload fed as complex<float> (what SDR++ hands the plugin): 9.17 instead of 3.17 algorithmic bytes per sample
         Sc, Kc = min(S, 256), min(K, 20)
