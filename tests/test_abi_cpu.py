@@ -107,3 +107,30 @@ def test_cpp_adapters_build_and_fail_loudly_without_gpu(dab):
             open(fin, "wb").write(b"\x00" * 64)
             res = subprocess.run([exe, "rs", fin, os.path.join(d, "out.bin")], capture_output=True, text=True, timeout=60)
             assert res.returncode == 3 and "no CPU fallback" in res.stderr
+
+
+def test_bench_reference_arm_line_and_no_cpu_fallback():
+    """bench.py's contract as far as it can be checked without a GPU: `--impl reference` prints ONE JSON line with the keys the driver
+    reads (same metric / unit / config as our arm, `impl`, `cpu_baseline` with kind / cores / sample and the per-core split, a zero-copy
+    `e2e`), and our own arm refuses to run without a CUDA device instead of computing anything on the CPU."""
+    import json
+    import subprocess
+    import sys
+    bench = os.path.join(ROOT, "bench.py")
+    res = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-800:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "dab_mode1_iq_msps" and d["unit"] == "MS/s" and d["higher_is_better"] is True
+    assert d["config"]["workload"] == "full_chain_mode1_1024_streams_per_gpu" and d["value"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and "fft_shim" in cb["sample"] or cb["kind"] == "port"
+    assert d["e2e"] == {"value": d["value"], "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if cb["kind"] == "reference" and cb.get("per_core"):
+        split = cb["per_core"]["ms_per_frame"]
+        assert abs(split["ofdm"] + split["fic"] + split["msc"] + split["dabplus_rs"] - split["total"]) < 0.05 * split["total"]
+    import torch
+    if not torch.cuda.is_available():
+        res = subprocess.run([sys.executable, bench, "--steps", "1"], capture_output=True, text=True, timeout=300)
+        assert res.returncode != 0 and "no CPU fallback" in (res.stderr + res.stdout)
