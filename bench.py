@@ -313,6 +313,62 @@ def spot_check(pkg, tx, np, torch, cyc, subs, local_rank, stream, n_check=3, n_f
                     "from a time de-interleaver that is only partly filled with real CIFs, in the reference exactly as here"}
 
 
+def channel_legs(pkg, tx, np, torch, local_rank, stream, n_streams=256, reps=6):
+    """BASELINE.json configs[2] / SURVEY.md section 8(d) config 3: the channel decoder alone on `n_streams` streams, soft bits already on the
+    device (dabgpu_softbits_push outside the timed region; every stream carries the same coded frames, noisy at 6 dB).  One timed unit =
+    dabgpu_chan_decode of one transmission frame of every stream (4 CIFs of every sub-channel + 4 FIB groups)."""
+    S = tx.Subchannel
+    ensembles = {
+        "a_18x_eep_3a_48cu": tx.default_ensemble(),
+        "b_eep_mix_1a_to_4b": [S(0, 0, 72, eep_level=0, dabplus=False), S(1, 72, 8, eep_level=1, dabplus=False), S(2, 80, 72, eep_level=1, dabplus=False),
+                               S(3, 152, 48, eep_level=2, dabplus=False), S(4, 200, 32, eep_level=3, dabplus=False),
+                               S(5, 232, 54, eep_level=0, eep_type_b=True, dabplus=False), S(6, 286, 42, eep_level=1, eep_type_b=True, dabplus=False),
+                               S(7, 328, 54, eep_level=2, eep_type_b=True, dabplus=False), S(8, 382, 45, eep_level=3, eep_type_b=True, dabplus=False),
+                               S(9, 427, 96, eep_level=2, dabplus=False), S(10, 523, 120, eep_level=1, dabplus=False), S(11, 643, 144, eep_level=0, dabplus=False),
+                               S(12, 787, 64, eep_level=3, dabplus=False)],
+        "c_uep_rows_0_14_37_63": [S(0, 0, 16, is_uep=True, uep_index=0, dabplus=False), S(1, 16, 32, is_uep=True, uep_index=14, dabplus=False),
+                                  S(2, 48, 140, is_uep=True, uep_index=37, dabplus=False), S(3, 188, 416, is_uep=True, uep_index=63, dabplus=False)],
+    }
+    out = {"streams": n_streams, "unit": "one transmission frame of every stream (4 CIFs of every sub-channel, 4 FIB groups)",
+           "input": "coded frames of the synthetic transmitter as int8 soft bits, AWGN 6 dB, resident in the frame ring before the timed region"}
+    for name, subs in ensembles.items():
+        ens = tx.EnsembleTx(1, subs, seed=21)
+        rng = np.random.default_rng(3)
+        frames = [tx.hard_to_soft(ens.next_frame_bits(), rng, snr_db=6.0) for _ in range(10)]
+        g = pkg.DabGpu(mode=1, max_streams=n_streams, device=local_rank, cuda_stream=stream.cuda_stream)
+        for s_ in range(n_streams):
+            g.msc_configure(s_, subs)
+        batch = [np.ascontiguousarray(np.broadcast_to(f, (n_streams, f.size))) for f in frames]
+        for i in range(6):                      # fills the 16-CIF time de-interleavers
+            g.softbits_push(batch[i])
+            g.chan_decode()
+        g.chan_join()
+        torch.cuda.synchronize()
+        c0 = g.counters()
+        total_ms, units = 0.0, 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for r in range(reps):
+            for i in range(4):
+                g.softbits_push(batch[(6 + 4 * r + i) % len(batch)])
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for i in range(4):
+                g.chan_decode()
+            g.chan_join()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+            units += 4
+        c1 = g.counters()
+        g.close()
+        bits = (c1["msc_bytes_decoded"] - c0["msc_bytes_decoded"]) * 8 + (c1["fibs_total"] - c0["fibs_total"]) * 256
+        steps = n_streams * units * (4 * 774 + 4 * sum(sum(n for _, n in sc.segments()) // 4 for sc in subs))
+        out[name] = {"sub_channels": len(subs), "capacity_units": sum(sc.length for sc in subs), "ms_per_unit": total_ms / units,
+                     "viterbi_mbit_s": bits / (total_ms * 1e-3) / 1e6, "trellis_steps_per_s": steps / (total_ms * 1e-3),
+                     "fibs_crc_ok": c1["fibs_crc_ok"] - c0["fibs_crc_ok"], "fibs_total": c1["fibs_total"] - c0["fibs_total"]}
+    return out
+
+
 def timed_pass(torch, dist, world, stream, step, K, finish=None, start=None):
     """K steps bracketed by barrier + synchronize, CUDA events on `stream`; returns ms (this rank)."""
     torch.cuda.synchronize()
@@ -345,6 +401,7 @@ def main():
     ap.add_argument("--no-spot-check", action="store_true")
     ap.add_argument("--no-ofdm-leg", action="store_true", help="full workload: skip the OFDM-only sub-leg")
     ap.add_argument("--contexts", type=int, default=1, help="device-resident legs: split the streams of a GPU over this many contexts (each with its own CUDA streams)")
+    ap.add_argument("--no-channel-leg", action="store_true", help="skip the channel-decode-only sub-legs (BASELINE configs[2])")
     ap.add_argument("--no-c32-leg", action="store_true", help="skip the OFDM-only sub-leg with complex<float> input (256 streams)")
     ap.add_argument("--wc-host", action="store_true", help="e2e: write-combined pinned memory for the IQ the host feeds in")
     args = ap.parse_args()
@@ -691,6 +748,13 @@ def main():
         line["ofdm_only_256"] = {"workload": "ofdm_demod_mode1_256_streams_per_gpu", "ms_per_step": ms_o / K,
                                  "iq_msps": world * 256 * FRAME_SAMPLES * K / (ms_o * 1e-3) / 1e6, "kernel_ms": {k: v["ms"] for k, v in leg["prof"].items()},
                                  "roofline": roofline_ofdm(leg["prof"], fr, leg["ms_prof"], n_streams=256)}
+    if full and not args.no_channel_leg and rank == 0:
+        # BASELINE.json configs[2]: MSC channel decode alone (time de-interleave + de-puncture + Viterbi + descramble, DAB+ RS where the
+        # sub-channel carries it) for the protection profiles of SURVEY.md section 8(d) config 3, 256 streams, soft bits pushed beforehand
+        try:
+            line["channel_decode"] = channel_legs(pkg, tx, np, torch, local_rank, stream)
+        except Exception as e:
+            line["channel_decode"] = {"error": str(e)[:200]}
     if not args.no_c32_leg:
         # the same OFDM workload fed as complex<float> (what SDR++ hands the plugin): 9.17 instead of 3.17 algorithmic bytes per sample
         Sc, Kc = min(S, 256), min(K, 20)
