@@ -5,7 +5,7 @@ cd $GRAFT_REPO_ROOT
 (time timeout 900 python bench.py) > gpurun_out/r3_bench_default.json 2> gpurun_out/r3_bench_default.err
 (time timeout 600 python bench.py --impl reference --steps 2 --warmup 1) > gpurun_out/r3_bench_reference.json 2> gpurun_out/r3_bench_reference.err
 cat gpurun_out/r3_pytest.log gpurun_out/r3_smoke.log
-tail -4 gpurun_out/r3_bench_default.err gpurun_out/r3_bench_reference.err
+tail -n 4 gpurun_out/r3_bench_default.err; tail -n 4 gpurun_out/r3_bench_reference.err
 python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/r3_bench_default.json").read().strip().splitlines()[-1])
