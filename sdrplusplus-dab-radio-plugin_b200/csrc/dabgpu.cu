@@ -404,6 +404,7 @@ struct VlBound {
     }
 };
 
+#define VIT_ORDER_MIN_JOBS 1024u   // calls with at least this many trellises that stay on k_viterbi are decoded longest first
 #ifndef VL_TB_WIDE
 #define VL_TB_WIDE 10u   // traceback rows per batch of the 128-register lane kernel (two batches in flight); 15 / 20 / 25 rows hide more of
                          // the decision loads' latency but spill in the forward loop: 1.26 / 1.25 / 1.39 ms against 1.13
@@ -411,6 +412,7 @@ struct VlBound {
 static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, const VlBound* bound, bool precounted = false) {
     CUDA_TRY(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
     VlPlan* plan = nullptr;
+    VlPlan* order_plan = nullptr;      // plan used only to order k_viterbi's queue
     uint32_t rows = 0, groups = 0, active = 0;
     bool lanes_wide = false;
     if (bound && !bound->oversize && ctx->vl_mode != 2) {
@@ -433,7 +435,29 @@ static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, 
             if ((rc = ctx->d_vllist.alloc(size_t(n_jobs) * 4))) return rc;
             if ((rc = ctx->d_vlsym.alloc(size_t(rows) * 128u))) return rc;
             plan = ctx->d_vlplan.as<VlPlan>();
+        } else if (active >= VIT_ORDER_MIN_JOBS) {
+            // too few trellises for the lane kernel, enough for the order to matter: k_viterbi pulls them longest first (below)
+            int rc;
+            if (ctx->d_vllist.bytes < size_t(n_jobs) * 4) CUDA_TRY(sync_ctx(ctx));
+            if ((rc = ctx->d_vllist.alloc(size_t(n_jobs) * 4))) return rc;
+            order_plan = ctx->d_vlplan.as<VlPlan>();
         }
+    }
+    if (order_plan) {
+        // A call that mixes short and long trellises (UEP row 63 is 9 222 steps, a FIB group 774) leaves its longest jobs to the end
+        // of k_viterbi's queue in job order, and the call then waits for a few warps walking the longest trellises alone.  The lane
+        // path's histogram and scatter give the job list by length class, longest first (1.11 instead of 1.35 ms for 256 streams of
+        // UEP rows 0 / 14 / 37 / 63: what remains is one warp's walk over 9 222 steps).  Scheduling only: every trellis is decoded by the same code.
+        ctx->prof.begin(PROF_CHAN_MISC, ctx->stream);
+        const int tb = 256, nb = (n_jobs + tb - 1) / tb;
+        if (!precounted) {
+            CUDA_TRY(cudaMemsetAsync(order_plan, 0, sizeof(VlPlan), ctx->stream));
+            k_vit_count<<<nb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, order_plan);
+        }
+        k_vit_plan<<<1, 32, 0, ctx->stream>>>(order_plan, 2 /* never the lane kernel */, 0u, 0u, 0u);
+        k_vit_scatter<<<nb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, order_plan, ctx->d_vllist.as<uint32_t>());
+        ctx->prof.end(ctx->stream);
+        ctx->launches += precounted ? 2 : 3;
     }
     if (plan) {
         static const VlConst kc = {0xFFFFFFFFu, 2u, 4u, 16u, 256u, 0x10000u};
@@ -482,7 +506,9 @@ static int launch_viterbi(dabgpu_ctx* ctx, const VitJobDev* d_jobs, int n_jobs, 
     }
     // the warp-per-trellis kernel takes the call when the plan says so (few trellises, or no plan at all)
     k_viterbi<<<ctx->vit_blocks, VIT_WARPS_PER_BLOCK * 32, VIT_SMEM_BYTES, ctx->stream>>>(d_jobs, n_jobs, ctx->d_counter.as<int>(), ctx->d_scratch.as<uint2>(),
-                                                                                       ctx->scratch_steps, ctx->d_prbs.as<uint32_t>(), ctx->chan.geom, reinterpret_cast<const uint32_t*>(plan));
+                                                                                       ctx->scratch_steps, ctx->d_prbs.as<uint32_t>(), ctx->chan.geom,
+                                                                                       reinterpret_cast<const uint32_t*>(plan ? plan : order_plan),
+                                                                                       (plan || order_plan) ? ctx->d_vllist.as<uint32_t>() : nullptr);
     ctx->prof.end(ctx->stream);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());

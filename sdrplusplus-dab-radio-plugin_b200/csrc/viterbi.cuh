@@ -414,9 +414,13 @@ __device__ void vit_decode_job(const VitJobDev& J, uint2* __restrict__ dec, uint
 // Persistent kernel: every warp pulls trellises from a global counter until none are left.
 __global__ void __launch_bounds__(VIT_WARPS_PER_BLOCK * 32)
 k_viterbi(const VitJobDev* __restrict__ jobs, const int n_jobs, int* __restrict__ counter, uint2* __restrict__ scratch,
-          const uint32_t scratch_steps, const uint32_t* __restrict__ prbs_words, const GatherGeom G, const uint32_t* __restrict__ lanes_plan) {
+          const uint32_t scratch_steps, const uint32_t* __restrict__ prbs_words, const GatherGeom G, const uint32_t* __restrict__ lanes_plan,
+          const uint32_t* __restrict__ order) {
     // lanes_plan[0] != 0: this call is decoded by k_viterbi_lanes (viterbi_lanes.cuh), decided on the device by k_vit_plan
     if (lanes_plan != nullptr && lanes_plan[0] != 0u) return;
+    // order != nullptr: the active jobs by length class, longest first (k_vit_scatter; VlPlan words 2 and 3 = n_active, oversize)
+    const bool ordered = order != nullptr && lanes_plan != nullptr && lanes_plan[3] == 0u;
+    const int n_pull = ordered ? int(lanes_plan[2]) : n_jobs;
     extern __shared__ __align__(16) uint8_t s_vit[];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t wib = threadIdx.x >> 5;
@@ -430,8 +434,8 @@ k_viterbi(const VitJobDev* __restrict__ jobs, const int n_jobs, int* __restrict_
         int job = 0;
         if (lane == 0) job = atomicAdd(counter, 1);
         job = __shfl_sync(FULL_MASK, job, 0);
-        if (job >= n_jobs) break;
-        const VitJobDev J = jobs[job];
+        if (job >= n_pull) break;
+        const VitJobDev J = jobs[ordered ? order[job] : uint32_t(job)];
         if (J.total_steps == 0) continue;
         __syncwarp();
         vit_fill_rowoff(J, G, s_rowoff, lane);

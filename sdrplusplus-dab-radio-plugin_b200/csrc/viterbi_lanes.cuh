@@ -27,7 +27,7 @@ __host__ __device__ inline uint32_t vl_bucket_cap(uint32_t b) { return b < 32u ?
 __host__ __device__ inline uint32_t vl_bucket_rows(uint32_t b) { return vl_bucket_cap(b) + VL_PAD_ROWS; }
 
 struct VlPlan {
-    uint32_t use_lanes, n_groups, n_active, oversize;
+    uint32_t use_lanes, n_groups, n_active, oversize;   // k_viterbi reads words 0, 2 and 3 through a plain uint32_t pointer
     uint32_t next_group;              // work counter of k_viterbi_lanes
     uint32_t has_m128;                // k_vit_prep found a -128 symbol in the call: the decoder takes the general branch-error form
     uint32_t pad_[2];
@@ -80,7 +80,7 @@ __global__ void k_vit_plan(VlPlan* __restrict__ plan, const int mode, const uint
 
 __global__ void k_vit_scatter(const VitJobDev* __restrict__ jobs, const int n_jobs, VlPlan* __restrict__ plan, uint32_t* __restrict__ list) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (!plan->use_lanes) return;
+    if (plan->oversize) return;     // a trellis beyond the classes: no list (k_viterbi then takes the jobs in index order)
     const uint32_t steps = gid < n_jobs ? jobs[gid].total_steps : 0u;
     const uint32_t b = steps != 0u ? vl_bucket(steps) : 0xFFFFFFFFu;
     // one cursor atomic per class and warp (see vl_count_warp); the lanes of the class take consecutive entries

@@ -123,6 +123,31 @@ def test_viterbi_lane_plan_edge_cases(gpu_ctx, tx, pyref):
     g.close()
 
 
+def test_viterbi_warp_kernel_longest_first_order(gpu_ctx, tx, pyref):
+    """A call of 1 024 .. 6 143 trellises stays on the warp-per-trellis kernel, which then pulls its jobs by length class, longest
+    first (launch_viterbi: order_plan).  Mixed lengths incl. UEP row 63 (9 222 steps) and partial classes; bytes and path errors
+    of every trellis equal the oracle's, and equal what the same call gives with the order switched off (vit-warps flag)."""
+    rng = np.random.default_rng(29)
+    port = pyref.PortViterbi()
+    kinds = [tx.FIC_SEGMENTS, tx.eep_segments(48, 2, False), tx.uep_segments(0), tx.uep_segments(14), tx.uep_segments(37), tx.eep_segments(8, 1, False),
+             tx.eep_segments(54, 2, True)]
+    segs = [kinds[i % len(kinds)] for i in range(1190)] + [tx.uep_segments(63)] * 10
+    order = rng.permutation(len(segs))
+    segs = [segs[i] for i in order]
+    softs = [np.clip(rng.normal(0.0, 60.0, size=int(tx.puncture_mask(sg).sum())), -127, 127).astype(np.int8) for sg in segs]
+    g = gpu_ctx.DabGpu(mode=1, max_streams=1)            # auto: 1 200 trellises < the lane kernel's threshold
+    outs, perr = g.viterbi_decode(softs, segs)
+    g.close()
+    g2 = gpu_ctx.DabGpu(mode=1, max_streams=1, flags=4)  # DABGPU_FLAG_VIT_LANES_NEVER: no plan at all, jobs in index order
+    outs2, perr2 = g2.viterbi_decode(softs, segs)
+    g2.close()
+    for i in range(len(segs)):
+        assert np.array_equal(outs[i], outs2[i]) and int(perr[i]) == int(perr2[i]), i
+    for i in list(range(0, len(segs), 7)) + [j for j, sg in enumerate(segs) if sum(n for _, n in sg) // 4 > 9000]:
+        exp, _, exp_err = port.decode(softs[i], segs[i])
+        assert np.array_equal(outs[i], exp) and int(perr[i]) == exp_err, i
+
+
 def test_viterbi_bad_arguments(gpu_ctx, tx):
     g = gpu_ctx.DabGpu(mode=1, max_streams=1)
     soft = np.zeros(100, dtype=np.int8)
